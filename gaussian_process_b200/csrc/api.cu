@@ -1,0 +1,234 @@
+// Handle management, error reporting, fused fit / fit+gradient drivers, host-buffer entry points and
+// the FP64 peak micro-benchmarks of libgpx.
+#include <stdarg.h>
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void gpx_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* gpx_last_error(void) { return g_err; }
+extern "C" int gpx_version(void) { return GPX_VERSION; }
+extern "C" int64_t gpx_padded_dim(int64_t n) { return ((n + GPX_T - 1) / GPX_T) * GPX_T; }
+
+extern "C" int gpx_create(int device, gpx_handle* out) {
+    GPX_REQUIRE(out != nullptr, 2);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        gpx_set_error("gpx_create: no CUDA device available (%s); libgpx has no CPU fallback", cudaGetErrorString(e));
+        return GPX_E_CUDA;
+    }
+    GPX_REQUIRE(device >= 0 && device < ndev, 1);
+    GPX_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    GPX_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        gpx_set_error("gpx_create: device %d is sm_%d%d; libgpx is built for sm_100a (B200) only", device, prop.major, prop.minor);
+        return GPX_E_CUDA;
+    }
+    gpx_ctx* h = new gpx_ctx();
+    memset(h, 0, sizeof(*h));
+    h->device = device;
+    h->stream = 0;
+    h->world = 1;
+    GPX_CUDA(cudaMalloc(&h->d_info, sizeof(int)));
+    GPX_CUDA(cudaMemset(h->d_info, 0, sizeof(int)));
+    GPX_CUDA(cudaMalloc(&h->d_theta, 16 * sizeof(double)));
+    GPX_CUDA(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+    GPX_CUDA(cudaEventCreateWithFlags(&h->ev_a, cudaEventDisableTiming));
+    GPX_CUDA(cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming));
+    *out = h;
+    return 0;
+}
+
+extern "C" int gpx_destroy(gpx_handle h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    if (h->scratch) cudaFree(h->scratch);
+    if (h->d_info) cudaFree(h->d_info);
+    if (h->d_partial) cudaFree(h->d_partial);
+    if (h->d_theta) cudaFree(h->d_theta);
+    if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+    if (h->ev_a) cudaEventDestroy(h->ev_a);
+    if (h->ev_b) cudaEventDestroy(h->ev_b);
+    delete h;
+    return 0;
+}
+
+extern "C" int gpx_set_stream(gpx_handle h, void* s) {
+    GPX_REQUIRE(h != nullptr, 1);
+    h->stream = (cudaStream_t)s;
+    return 0;
+}
+
+extern "C" int gpx_synchronize(gpx_handle h) {
+    GPX_REQUIRE(h != nullptr, 1);
+    GPX_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int64_t gpx_launch_count(gpx_handle h) { return h ? h->launches : 0; }
+
+int gpx_scratch(gpx_ctx* h, size_t bytes, void** out) {
+    if (h->scratch_bytes < bytes) {
+        if (h->scratch) {
+            cudaStreamSynchronize(h->stream);
+            cudaFree(h->scratch);
+            h->scratch = nullptr;
+            h->scratch_bytes = 0;
+        }
+        cudaError_t e = cudaMalloc(&h->scratch, bytes);
+        if (e != cudaSuccess) {
+            gpx_set_error("gpx: cudaMalloc(%zu) for scratch failed: %s", bytes, cudaGetErrorString(e));
+            return GPX_E_NOMEM;
+        }
+        h->scratch_bytes = bytes;
+    }
+    *out = h->scratch;
+    return 0;
+}
+
+int gpx_read_info(gpx_ctx* h, int* info_host) {
+    GPX_CUDA(cudaMemcpyAsync(info_host, h->d_info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    GPX_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused drivers
+// ---------------------------------------------------------------------------------------------
+extern "C" int gpx_gp_fit(gpx_handle h, int kind, const double* X, int64_t n, int D, const double* theta_host, int ntheta,
+                          double s, const double* y, double* A, int64_t np_, int64_t lda, double* dinv, double* alpha,
+                          double* out3) {
+    GPX_REQUIRE(h != nullptr, 1);
+    GPX_REQUIRE(np_ == gpx_padded_dim(n), 11);
+    // K + s I, lower tiles only, identity padding            (tune...:306-307, CO2...:142-143)
+    GPX_TRY(gpx_cov_build(h, kind, X, n, X, n, D, theta_host, ntheta, s, GPX_COV_SAME_X | GPX_COV_LOWER, A, np_, np_, lda,
+                          nullptr, 0));
+    int info = gpx_potrf(h, A, np_, lda, dinv);
+    if (info != 0) return info;
+    // alpha = L^-T (L^-1 y)                                   (tune...:308-309)
+    GPX_CUDA(cudaMemsetAsync(alpha, 0, np_ * sizeof(double), h->stream));
+    GPX_CUDA(cudaMemcpyAsync(alpha, y, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    GPX_TRY(gpx_trsv(h, A, np_, lda, dinv, 0, alpha));
+    GPX_TRY(gpx_trsv(h, A, np_, lda, dinv, 1, alpha));
+    return gpx_lml(h, A, n, lda, y, alpha, out3);            // tune...:312
+}
+
+extern "C" int gpx_gp_fit_grad(gpx_handle h, int kind, const double* X, int64_t n, int D, const double* theta_host,
+                               int ntheta, double s, const double* y, double* A, int64_t np_, int64_t lda, double* dinv,
+                               double* Kinv, double* alpha, double* out3, double* grad) {
+    int r = gpx_gp_fit(h, kind, X, n, D, theta_host, ntheta, s, y, A, np_, lda, dinv, alpha, out3);
+    if (r != 0) return r;
+    // K_y^-1 = L^-T L^-1 (tune...:144): in-place triangular inverse, then one triangular SYRK into Kinv.
+    // Kinv doubles as the trtri workspace (it is overwritten by lauum afterwards).
+    GPX_TRY(gpx_trtri(h, A, np_, lda, dinv, Kinv));
+    GPX_TRY(gpx_lauum(h, A, np_, lda, Kinv, lda));
+    return gpx_lml_grad(h, kind, X, n, D, theta_host, ntheta, Kinv, lda, alpha, grad);  // tune...:43-57
+}
+
+extern "C" int gpx_host_lml(gpx_handle h, int kind, const double* X, int64_t n, int D, const double* theta, int ntheta,
+                            double s, const double* y, double* lml_out, double* grad_host) {
+    GPX_REQUIRE(h != nullptr, 1);
+    GPX_REQUIRE(n > 0, 4);
+    const int64_t np_ = gpx_padded_dim(n);
+    const int64_t nt = np_ / GPX_T;
+    size_t bytes_A = (size_t)np_ * np_ * sizeof(double);
+    size_t bytes = bytes_A * (grad_host ? 2 : 1) + (size_t)nt * GPX_T * GPX_T * sizeof(double) +
+                   ((size_t)n * D + 2 * np_ + 32) * sizeof(double);
+    void* base = nullptr;
+    GPX_TRY(gpx_scratch(h, bytes, &base));
+    double* A = (double*)base;
+    double* Kinv = grad_host ? A + (size_t)np_ * np_ : nullptr;
+    double* dinv = A + (size_t)np_ * np_ * (grad_host ? 2 : 1);
+    double* dX = dinv + (size_t)nt * GPX_T * GPX_T;
+    double* dy = dX + (size_t)n * D;
+    double* dalpha = dy + np_;
+    double* dout = dalpha + np_;
+    GPX_CUDA(cudaMemcpyAsync(dX, X, (size_t)n * D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    GPX_CUDA(cudaMemcpyAsync(dy, y, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    int r;
+    if (grad_host)
+        r = gpx_gp_fit_grad(h, kind, dX, n, D, theta, ntheta, s, dy, A, np_, np_, dinv, Kinv, dalpha, dout, dout + 3);
+    else
+        r = gpx_gp_fit(h, kind, dX, n, D, theta, ntheta, s, dy, A, np_, np_, dinv, dalpha, dout);
+    if (r != 0) return r;
+    double host[3 + 11];
+    GPX_CUDA(cudaMemcpyAsync(host, dout, (3 + (grad_host ? ntheta : 0)) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    GPX_CUDA(cudaStreamSynchronize(h->stream));
+    *lml_out = host[0];
+    if (grad_host)
+        for (int i = 0; i < ntheta; ++i) grad_host[i] = host[3 + i];
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP64 peak micro-benchmarks (register-resident issue loops)
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* out) {
+    double c[16][2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i][0] = c[i][1] = 0.0;
+    double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                         : "+d"(c[i][0]), "+d"(c[i][1])
+                         : "d"(a), "d"(b));
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i][0] + c[i][1];
+    if (s == 12345.678) out[0] = s;
+}
+__global__ void __launch_bounds__(256) dfma_peak_kernel(int iters, double* out) {
+    double c[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i] = threadIdx.x * 1e-3 + i;
+    double a = 1.0 + threadIdx.x * 1e-9, b = 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) c[i] = fma(c[i], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i];
+    if (s == 12345.678) out[0] = s;
+}
+}  // namespace
+
+extern "C" int gpx_bench_fp64_peak(gpx_handle h, int use_dmma, int iters, double* tflops_out, double* ms_out) {
+    GPX_REQUIRE(h != nullptr, 1);
+    cudaEvent_t e0, e1;
+    GPX_CUDA(cudaEventCreate(&e0));
+    GPX_CUDA(cudaEventCreate(&e1));
+    const int blocks = 148 * 4, threads = 256;
+    double best = 1e30;
+    for (int rep = 0; rep < 4; ++rep) {
+        GPX_CUDA(cudaEventRecord(e0, h->stream));
+        if (use_dmma) dmma_peak_kernel<<<blocks, threads, 0, h->stream>>>(iters, h->d_theta);
+        else dfma_peak_kernel<<<blocks, threads, 0, h->stream>>>(iters, h->d_theta);
+        GPX_CHECK_LAUNCH(h);
+        GPX_CUDA(cudaEventRecord(e1, h->stream));
+        GPX_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        GPX_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double warps = (double)blocks * threads / 32.0;
+    const double flops = use_dmma ? warps * iters * 16.0 * 512.0 : warps * iters * 16.0 * 64.0;
+    *ms_out = best;
+    *tflops_out = flops / (best * 1e-3) / 1e12;
+    return 0;
+}

@@ -1,0 +1,77 @@
+// Shared declarations for libgpx (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/gpx.h"
+
+#define GPX_T 128  // tile edge used by every dense kernel
+
+struct gpx_ctx {
+    int device;
+    cudaStream_t stream;
+    int64_t launches;
+    // scratch owned by the handle (grown on demand)
+    void* scratch;       size_t scratch_bytes;
+    int* d_info;         // device int: first failing pivot (1-based) or 0
+    double* d_partial;   // reduction partials
+    size_t partial_elems;
+    double* d_theta;     // 16 doubles of hyper-parameters for kernels
+    // NCCL (optional, dlopen'ed)
+    void* nccl_comm; int rank, world;
+    cudaStream_t aux_stream; cudaEvent_t ev_a, ev_b;
+};
+
+void gpx_set_error(const char* fmt, ...);
+
+#define GPX_CUDA(call)                                                                       \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess) {                                                            \
+            gpx_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return GPX_E_CUDA;                                                               \
+        }                                                                                    \
+    } while (0)
+
+#define GPX_CHECK_LAUNCH(h)                                                                  \
+    do {                                                                                     \
+        (h)->launches++;                                                                     \
+        cudaError_t e__ = cudaGetLastError();                                                \
+        if (e__ != cudaSuccess) {                                                            \
+            gpx_set_error("%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            return GPX_E_CUDA;                                                               \
+        }                                                                                    \
+    } while (0)
+
+#define GPX_REQUIRE(cond, argno)                                                             \
+    do {                                                                                     \
+        if (!(cond)) {                                                                       \
+            gpx_set_error("%s:%d bad argument %d: %s", __FILE__, __LINE__, (argno), #cond);  \
+            return -(argno);                                                                 \
+        }                                                                                    \
+    } while (0)
+
+#define GPX_TRY(call)                                                                        \
+    do {                                                                                     \
+        int r__ = (call);                                                                    \
+        if (r__ != 0) return r__;                                                            \
+    } while (0)
+
+// ---- internal (C++) interfaces between translation units -------------------------------------
+struct GemmArgs {
+    const double* A; const double* B; double* C;
+    int M, N, K;                // M,N multiples of 128; K multiple of 16
+    int64_t lda, ldb, ldc;
+    double alpha, beta;
+    int64_t sA, sB, sC; int batch;   // strided batch (elements)
+    int a_kmajor, b_kmajor;     // 1: operand stored with k contiguous ([M][K] / [N][K]); 0: [K][M] / [K][N]
+    int lower_only;             // skip output tiles strictly above the diagonal
+    int kb_mode;                // first k: 0 -> 0, 1 -> tile row0, 2 -> tile col0
+    int ke_mode;                // last  k: 0 -> K, 1 -> tile row0+128, 2 -> tile col0+128
+    int rev_rows;               // schedule tile rows in reverse (longest k-loops first)
+};
+int gpx_gemm_launch(gpx_ctx* h, const GemmArgs& a);
+
+int gpx_scratch(gpx_ctx* h, size_t bytes, void** out);
+int gpx_read_info(gpx_ctx* h, int* info_host);

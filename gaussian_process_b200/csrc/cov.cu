@@ -1,0 +1,347 @@
+// Fused covariance-matrix builder and fused LML-gradient kernel.
+//
+// cov_build : one pass computes pairwise squared distances on 128x128 output tiles (X tiles staged in
+//             shared memory, X2 transposed so lane-contiguous reads are conflict free), applies the
+//             covariance family (SE / linear / periodic / CO2 composite = SE + SE*periodic + RQ + SE +
+//             delta), adds the noise diagonal, writes identity padding, and optionally emits every
+//             dK/dtheta_j in the same pass.  HBM-write bound: 8*n1p*n2p bytes.
+// lml_grad  : reads K^-1 once (lower tiles), recomputes dK/dtheta_j per element from X and accumulates
+//             .5 * sum (alpha_i alpha_j - Kinv_ij) dK_ij for all theta at once.  HBM-read bound.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TM = 128, TN = 128, DCH = 16, CTHREADS = 512, RI = 8;  // thread owns RI x 4 outputs
+constexpr double PI_D = 3.141592653589793238462643383279502884;  // == np.pi
+
+struct CovParams {
+    int kind, ntheta, D;
+    double th[11];
+};
+
+template <int KIND>
+struct NTheta { static constexpr int value = KIND == GPX_COV_SE ? 2 : KIND == GPX_COV_LIN ? 1 : KIND == GPX_COV_PER ? 2 : 11; };
+
+// value and derivatives of one covariance entry.  `acc` is the squared distance (or, for LIN, the
+// centred dot product); `aux` is sum_d (a_d + b_d) for LIN's derivative; diag = (same_x && i == j).
+template <int KIND, bool WITH_DK>
+__device__ __forceinline__ double cov_eval(const CovParams& p, double acc, double aux, bool diag, double* dk) {
+    if (KIND == GPX_COV_SE) {
+        const double sigma = p.th[0], l = p.th[1];
+        const double e = exp(-.5 * (1.0 / (l * l)) * acc);  // GP_regression.py:19
+        if (WITH_DK) {
+            dk[0] = 2.0 * sigma * e;                          // tune...:48
+            dk[1] = (sigma * sigma) * e * (acc / (l * l * l));  // tune...:54
+        }
+        return (sigma * sigma) * e;
+    } else if (KIND == GPX_COV_LIN) {
+        if (WITH_DK) dk[0] = -(aux - 2.0 * p.D * p.th[0]);
+        return acc;                                           // GP_regression.py:32
+    } else if (KIND == GPX_COV_PER) {
+        const double per = p.th[0], l = p.th[1];
+        const double r = sqrt(acc);
+        const double sn = sin(PI_D * r / per);
+        const double k = exp(-2.0 * (sn * sn) / (l * l));     // GP_regression.py:49
+        if (WITH_DK) {
+            dk[0] = k * (2.0 * PI_D * r / (per * per * l * l)) * sin(2.0 * PI_D * r / per);
+            dk[1] = k * 4.0 * (sn * sn) / (l * l * l);
+        }
+        return k;
+    } else {  // CO2 composite, CO2_example.py:9-94
+        const double* t = p.th;
+        const double d = acc;
+        const double r = sqrt(d);
+        const double e1 = exp(-.5 * d / (t[1] * t[1]));                       // :17
+        const double sn = sin(PI_D * r);
+        const double q = sn / t[4];
+        const double e2 = exp(-.5 * d / (t[3] * t[3]) + -2.0 * (q * q));      // :30-32
+        const double u = 1.0 + .5 * d / (t[7] * (t[6] * t[6]));               // :44
+        const double pw = 1.0 / pow(u, t[7]);                                 // :45
+        const double e4 = exp(-.5 * d / (t[9] * t[9]));                       // :65
+        const double k1 = (t[0] * t[0]) * e1;
+        const double k2 = (t[2] * t[2]) * e2;
+        const double k3 = (t[5] * t[5]) * pw;
+        double k4 = (t[8] * t[8]) * e4;
+        if (diag) k4 += t[10] * t[10];                                        // :66 (delta iff square block)
+        if (WITH_DK) {
+            dk[0] = 2.0 * t[0] * e1;
+            dk[1] = k1 * d / (t[1] * t[1] * t[1]);
+            dk[2] = 2.0 * k2 / t[2];
+            dk[3] = k2 * d / (t[3] * t[3] * t[3]);
+            dk[4] = k2 * 4.0 * (sn * sn) / (t[4] * t[4] * t[4]);
+            dk[5] = 2.0 * k3 / t[5];
+            dk[6] = k3 * d / (t[6] * t[6] * t[6] * u);
+            dk[7] = k3 * (-log(u) + (u - 1.0) / u);
+            dk[8] = 2.0 * t[8] * e4;
+            dk[9] = (t[8] * t[8]) * e4 * d / (t[9] * t[9] * t[9]);
+            dk[10] = diag ? 2.0 * t[10] : 0.0;
+        }
+        return ((k1 + k2) + k3) + k4;                                         // :90-93 (left-to-right sum)
+    }
+}
+
+// Accumulate pairwise terms for a 128x128 tile: thread (tx = tid&31, ty = tid>>5) owns rows ty+16i (i<8)
+// and columns tx+32j (j<4).  xs1: [128][DCH] row tile, xs2: [DCH][128] transposed column tile.
+template <int KIND>
+__device__ __forceinline__ void tile_accumulate(const CovParams& p, const double* __restrict__ X1, int64_t n1,
+                                                const double* __restrict__ X2, int64_t n2, int row0, int col0,
+                                                double* xs1, double* xs2, double (&acc)[RI][4], double (&aux)[RI][4]) {
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const int D = p.D;
+#pragma unroll
+    for (int i = 0; i < RI; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = aux[i][j] = 0.0;
+    for (int d0 = 0; d0 < D; d0 += DCH) {
+        const int dc = (D - d0) < DCH ? (D - d0) : DCH;
+        __syncthreads();
+        for (int idx = tid; idx < TM * dc; idx += CTHREADS) {
+            int r = idx / dc, dd = idx - r * dc;
+            int64_t gr = row0 + r;
+            xs1[r * DCH + dd] = gr < n1 ? X1[gr * D + d0 + dd] : 0.0;
+        }
+        for (int idx = tid; idx < TN * dc; idx += CTHREADS) {
+            int c = idx / dc, dd = idx - c * dc;
+            int64_t gc = col0 + c;
+            xs2[dd * TN + c] = gc < n2 ? X2[gc * D + d0 + dd] : 0.0;
+        }
+        __syncthreads();
+        for (int dd = 0; dd < dc; ++dd) {
+            double b[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = xs2[dd * TN + tx + 32 * j];
+#pragma unroll
+            for (int i = 0; i < RI; ++i) {
+                const double a = xs1[(ty + 16 * i) * DCH + dd];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (KIND == GPX_COV_LIN) {
+                        acc[i][j] += (a - p.th[0]) * (b[j] - p.th[0]);
+                        aux[i][j] += a + b[j];
+                    } else {
+                        const double df = a - b[j];
+                        acc[i][j] += df * df;
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int KIND, bool WITH_DK>
+__global__ void __launch_bounds__(CTHREADS) cov_build_kernel(CovParams p, const double* __restrict__ X1, int64_t n1,
+                                                            const double* __restrict__ X2, int64_t n2, double diag_add,
+                                                            int flags, double* __restrict__ K, int64_t ldk,
+                                                            double* __restrict__ dK, int64_t dk_stride) {
+    __shared__ double xs1[TM * DCH];
+    __shared__ double xs2[DCH * TN];
+    const int row0 = blockIdx.y * TM, col0 = blockIdx.x * TN;
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const bool same = flags & GPX_COV_SAME_X;
+    if ((flags & GPX_COV_LOWER) && col0 > row0) {  // strictly-upper tile: zeros
+#pragma unroll
+        for (int i = 0; i < RI; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int64_t off = (int64_t)(row0 + ty + 16 * i) * ldk + col0 + tx + 32 * j;
+                K[off] = 0.0;
+                if (WITH_DK) {
+#pragma unroll
+                    for (int q = 0; q < NTheta<KIND>::value; ++q) dK[q * dk_stride + off] = 0.0;
+                }
+            }
+        return;
+    }
+    double acc[RI][4], aux[RI][4];
+    tile_accumulate<KIND>(p, X1, n1, X2, n2, row0, col0, xs1, xs2, acc, aux);
+#pragma unroll
+    for (int i = 0; i < RI; ++i) {
+        const int64_t r = row0 + ty + 16 * i;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t c = col0 + tx + 32 * j;
+            const int64_t off = r * ldk + c;
+            double dk[11];
+            double v;
+            if (r < n1 && c < n2) {
+                const bool diag = same && (r == c);
+                double a = acc[i][j];
+                v = cov_eval<KIND, WITH_DK>(p, a, aux[i][j], diag, dk);
+                if (diag) v += diag_add;
+            } else {
+                v = (same && r == c) ? 1.0 : 0.0;
+                if (WITH_DK) {
+#pragma unroll
+                    for (int q = 0; q < NTheta<KIND>::value; ++q) dk[q] = 0.0;
+                }
+            }
+            K[off] = v;
+            if (WITH_DK) {
+#pragma unroll
+                for (int q = 0; q < NTheta<KIND>::value; ++q) dK[q * dk_stride + off] = dk[q];
+            }
+        }
+    }
+}
+
+// grad partials: partial[block][q] = sum over this lower tile of w_ij * dK_ij,q
+template <int KIND>
+__global__ void __launch_bounds__(CTHREADS) lml_grad_kernel(CovParams p, const double* __restrict__ X, int64_t n,
+                                                           const double* __restrict__ Kinv, int64_t ldk,
+                                                           const double* __restrict__ alpha, double* __restrict__ partial) {
+    __shared__ double xs1[TM * DCH];
+    __shared__ double xs2[DCH * TN];
+    __shared__ double red[CTHREADS / 32][11];
+    const int bm = blockIdx.y, bn = blockIdx.x;
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const int block_id = blockIdx.y * gridDim.x + blockIdx.x;
+    constexpr int NTH = NTheta<KIND>::value;
+    double sums[NTH];
+#pragma unroll
+    for (int q = 0; q < NTH; ++q) sums[q] = 0.0;
+    if (bn <= bm) {
+        const int row0 = bm * TM, col0 = bn * TN;
+        double acc[RI][4], aux[RI][4];
+        tile_accumulate<KIND>(p, X, n, X, n, row0, col0, xs1, xs2, acc, aux);
+        const double wmul = (bn == bm) ? 0.5 : 1.0;  // .5 * (1 on diagonal tiles | 2 on strictly-lower tiles)
+        double aj[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t c = col0 + tx + 32 * j;
+            aj[j] = c < n ? alpha[c] : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < RI; ++i) {
+            const int64_t r = row0 + ty + 16 * i;
+            const double ai = r < n ? alpha[r] : 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t c = col0 + tx + 32 * j;
+                if (r < n && c < n) {
+                    double dk[11];
+                    (void)cov_eval<KIND, true>(p, acc[i][j], aux[i][j], r == c, dk);
+                    const double w = wmul * (ai * aj[j] - Kinv[r * ldk + c]);
+#pragma unroll
+                    for (int q = 0; q < NTH; ++q) sums[q] += w * dk[q];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < NTH; ++q) {
+        double v = sums[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (tx == 0) red[ty][q] = v;
+    }
+    __syncthreads();
+    if (tid < p.ntheta) {
+        double v = 0.0;
+        for (int w = 0; w < CTHREADS / 32; ++w) v += red[w][tid];
+        partial[(int64_t)block_id * p.ntheta + tid] = v;
+    }
+}
+
+__global__ void grad_finish_kernel(int nblocks, int ntheta, const double* __restrict__ partial, double* __restrict__ grad) {
+    __shared__ double red[256];
+    const int q = blockIdx.x;
+    double s = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += 256) s += partial[(int64_t)b * ntheta + q];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) grad[q] = red[0];
+}
+
+int expected_ntheta(int kind) {
+    switch (kind) {
+        case GPX_COV_SE: return 2;
+        case GPX_COV_LIN: return 1;
+        case GPX_COV_PER: return 2;
+        case GPX_COV_CO2: return 11;
+    }
+    return -1;
+}
+
+int make_params(int kind, int D, const double* theta, int ntheta, CovParams* p) {
+    GPX_REQUIRE(expected_ntheta(kind) == ntheta, 7);
+    GPX_REQUIRE(D >= 1, 5);
+    p->kind = kind;
+    p->ntheta = ntheta;
+    p->D = D;
+    for (int i = 0; i < 11; ++i) p->th[i] = i < ntheta ? theta[i] : 0.0;
+    return 0;
+}
+
+template <bool WITH_DK>
+int launch_build(gpx_ctx* h, const CovParams& p, const double* X1, int64_t n1, const double* X2, int64_t n2, double diag_add,
+                 int flags, double* K, int64_t n1p, int64_t n2p, int64_t ldk, double* dK, int64_t dk_stride) {
+    dim3 grid((unsigned)(n2p / TN), (unsigned)(n1p / TM));
+    switch (p.kind) {
+        case GPX_COV_SE:
+            cov_build_kernel<GPX_COV_SE, WITH_DK><<<grid, CTHREADS, 0, h->stream>>>(p, X1, n1, X2, n2, diag_add, flags, K, ldk, dK, dk_stride);
+            break;
+        case GPX_COV_LIN:
+            cov_build_kernel<GPX_COV_LIN, WITH_DK><<<grid, CTHREADS, 0, h->stream>>>(p, X1, n1, X2, n2, diag_add, flags, K, ldk, dK, dk_stride);
+            break;
+        case GPX_COV_PER:
+            cov_build_kernel<GPX_COV_PER, WITH_DK><<<grid, CTHREADS, 0, h->stream>>>(p, X1, n1, X2, n2, diag_add, flags, K, ldk, dK, dk_stride);
+            break;
+        default:
+            cov_build_kernel<GPX_COV_CO2, WITH_DK><<<grid, CTHREADS, 0, h->stream>>>(p, X1, n1, X2, n2, diag_add, flags, K, ldk, dK, dk_stride);
+            break;
+    }
+    GPX_CHECK_LAUNCH(h);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int gpx_cov_build(gpx_handle h, int kind, const double* X1, int64_t n1, const double* X2, int64_t n2, int D,
+                             const double* theta_host, int ntheta, double diag_add, int flags, double* K, int64_t n1p,
+                             int64_t n2p, int64_t ldk, double* dK, int64_t dk_stride) {
+    GPX_REQUIRE(h != nullptr, 1);
+    GPX_REQUIRE(kind >= 0 && kind <= 3, 2);
+    GPX_REQUIRE(n1 > 0 && n2 > 0, 4);
+    GPX_REQUIRE(n1p >= n1 && n1p % TM == 0 && n2p >= n2 && n2p % TN == 0, 13);
+    GPX_REQUIRE(ldk >= n2p, 15);
+    GPX_REQUIRE(!(flags & GPX_COV_SAME_X) || (n1 == n2), 11);
+    CovParams p;
+    GPX_TRY(make_params(kind, D, theta_host, ntheta, &p));
+    if (dK) return launch_build<true>(h, p, X1, n1, X2, n2, diag_add, flags, K, n1p, n2p, ldk, dK, dk_stride);
+    return launch_build<false>(h, p, X1, n1, X2, n2, diag_add, flags, K, n1p, n2p, ldk, nullptr, 0);
+}
+
+extern "C" int gpx_lml_grad(gpx_handle h, int kind, const double* X, int64_t n, int D, const double* theta_host, int ntheta,
+                            const double* Kinv, int64_t ldk, const double* alpha, double* grad) {
+    GPX_REQUIRE(h != nullptr, 1);
+    GPX_REQUIRE(kind >= 0 && kind <= 3, 2);
+    CovParams p;
+    GPX_TRY(make_params(kind, D, theta_host, ntheta, &p));
+    const int nt = (int)((n + TM - 1) / TM);
+    const size_t need = (size_t)nt * nt * ntheta;
+    if (h->partial_elems < need) {
+        if (h->d_partial) cudaFree(h->d_partial);
+        h->d_partial = nullptr;
+        h->partial_elems = 0;
+        if (cudaMalloc(&h->d_partial, need * sizeof(double)) != cudaSuccess) {
+            gpx_set_error("cudaMalloc of %zu gradient partials failed", need);
+            return GPX_E_NOMEM;
+        }
+        h->partial_elems = need;
+    }
+    dim3 grid(nt, nt);
+    switch (kind) {
+        case GPX_COV_SE: lml_grad_kernel<GPX_COV_SE><<<grid, CTHREADS, 0, h->stream>>>(p, X, n, Kinv, ldk, alpha, h->d_partial); break;
+        case GPX_COV_LIN: lml_grad_kernel<GPX_COV_LIN><<<grid, CTHREADS, 0, h->stream>>>(p, X, n, Kinv, ldk, alpha, h->d_partial); break;
+        case GPX_COV_PER: lml_grad_kernel<GPX_COV_PER><<<grid, CTHREADS, 0, h->stream>>>(p, X, n, Kinv, ldk, alpha, h->d_partial); break;
+        default: lml_grad_kernel<GPX_COV_CO2><<<grid, CTHREADS, 0, h->stream>>>(p, X, n, Kinv, ldk, alpha, h->d_partial); break;
+    }
+    GPX_CHECK_LAUNCH(h);
+    grad_finish_kernel<<<ntheta, 256, 0, h->stream>>>(nt * nt, ntheta, h->d_partial, grad);
+    GPX_CHECK_LAUNCH(h);
+    return 0;
+}

@@ -1,0 +1,185 @@
+// FP64 tensor-core GEMM for sm_100a: C = alpha * op(A) op(B) + beta * C on 128x128 tiles.
+//
+// Tensor path: mma.sync.aligned.m8n8k4.f64 (SASS DMMA.8x8x4 -- the only FP64 tensor instruction on
+// sm_100a; tcgen05.mma has no f64 kind).  One CTA = 8 warps (2 x 4), warp tile 64 x 32 =
+// 8 x 4 DMMA fragments (32 independent accumulators per warp), K slab 16, 4-stage cp.async
+// (LDGSTS) pipeline into padded shared memory laid out so every 64-bit fragment load is
+// bank-conflict free:
+//   k-major operand  : smem[row][16+4]   lane(g,t) reads [r0+g][kk+t]  -> bank8 = 4g+t   (distinct)
+//   k-strided operand: smem[k][128+4]    lane(g,t) reads [kk+t][c0+g]  -> bank8 = 4t+g   (distinct)
+// This kernel is the trailing update (SYRK/GEMM), the TRSM/TRTRI/LAUUM work-horse and the
+// prediction TRSM; triangular structure is exploited at tile granularity through per-tile k ranges.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, NTHREADS = 256;
+constexpr int KC_LD = BK + 4;       // 20 doubles
+constexpr int KS_LD = 128 + 4;      // 132 doubles
+constexpr int OP_ELEMS = 128 * KC_LD;  // 2560 doubles per operand per stage (>= 16*132)
+constexpr int SMEM_BYTES = STAGES * 2 * OP_ELEMS * (int)sizeof(double);  // 163840
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// global -> shared for one operand slab.  KMAJOR: 128 rows x 16 k (row r = P[(r0+r)*ld + k0 ..]);
+// else 16 k-rows x 128 (row kr = P[(k0+kr)*ld + r0 ..]).
+template <bool KMAJOR>
+__device__ __forceinline__ void load_slab(double* s, const double* __restrict__ P, int64_t ld, int r0, int k0, int tid) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int id = tid + i * NTHREADS;  // 0..1023 16-byte chunks
+        if (KMAJOR) {
+            int r = id >> 3, c = id & 7;
+            cp_async16(s + r * KC_LD + c * 2, P + (int64_t)(r0 + r) * ld + k0 + c * 2);
+        } else {
+            int kr = id >> 6, c = id & 63;
+            cp_async16(s + kr * KS_LD + c * 2, P + (int64_t)(k0 + kr) * ld + r0 + c * 2);
+        }
+    }
+}
+
+template <bool A_KM, bool B_KM>
+__global__ void __launch_bounds__(NTHREADS, 1) dgemm_dmma_kernel(GemmArgs p) {
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x;
+    const int bn = blockIdx.x;
+    const int bm = p.rev_rows ? (gridDim.y - 1 - blockIdx.y) : blockIdx.y;
+    if (p.lower_only && bn > bm) return;
+    const int row0 = bm * BM, col0 = bn * BN;
+    const double* __restrict__ A = p.A + (int64_t)blockIdx.z * p.sA;
+    const double* __restrict__ B = p.B + (int64_t)blockIdx.z * p.sB;
+    double* C = p.C + (int64_t)blockIdx.z * p.sC;
+
+    int kbeg = p.kb_mode == 1 ? row0 : (p.kb_mode == 2 ? col0 : 0);
+    int kend = p.ke_mode == 1 ? row0 + BM : (p.ke_mode == 2 ? col0 + BN : p.K);
+    if (kend > p.K) kend = p.K;
+    const int nk = kend > kbeg ? (kend - kbeg) / BK : 0;
+
+    const int warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm0 = (warp >> 2) * 64, wn0 = (warp & 3) * 32;
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    auto sA = [&](int st) { return smem + (st * 2 + 0) * OP_ELEMS; };
+    auto sB = [&](int st) { return smem + (st * 2 + 1) * OP_ELEMS; };
+
+    // prologue: prefetch STAGES-1 slabs
+#pragma unroll
+    for (int st = 0; st < STAGES - 1; ++st) {
+        if (st < nk) {
+            load_slab<A_KM>(sA(st), A, p.lda, row0, kbeg + st * BK, tid);
+            load_slab<B_KM>(sB(st), B, p.ldb, col0, kbeg + st * BK, tid);
+        }
+        cp_async_commit();
+    }
+
+    for (int kt = 0; kt < nk; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            int nxt = kt + STAGES - 1;
+            if (nxt < nk) {
+                int st = nxt % STAGES;
+                load_slab<A_KM>(sA(st), A, p.lda, row0, kbeg + nxt * BK, tid);
+                load_slab<B_KM>(sB(st), B, p.ldb, col0, kbeg + nxt * BK, tid);
+            }
+            cp_async_commit();
+        }
+        const double* a_s = sA(kt % STAGES);
+        const double* b_s = sB(kt % STAGES);
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += 4) {
+            double af[8], bf[4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                af[i] = A_KM ? a_s[(wm0 + i * 8 + g) * KC_LD + kk + t] : a_s[(kk + t) * KS_LD + wm0 + i * 8 + g];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                bf[j] = B_KM ? b_s[(wn0 + j * 8 + g) * KC_LD + kk + t] : b_s[(kk + t) * KS_LD + wn0 + j * 8 + g];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    cp_async_wait<0>();
+    // all of this CTA's operand reads have landed before any of its stores: in-place use is safe when
+    // the operand tile the CTA reads is exactly its own output tile (TRSM leaves).
+    __syncthreads();
+
+    const double alpha = p.alpha, beta = p.beta;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = row0 + wm0 + i * 8 + g;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = col0 + wn0 + j * 8 + 2 * t;
+            double2* dst = reinterpret_cast<double2*>(C + (int64_t)r * p.ldc + c);
+            double2 v;
+            v.x = alpha * acc[i][j][0];
+            v.y = alpha * acc[i][j][1];
+            if (beta != 0.0) {
+                double2 o = *dst;
+                v.x += beta * o.x;
+                v.y += beta * o.y;
+            }
+            *dst = v;
+        }
+    }
+}
+
+template <bool A_KM, bool B_KM>
+int launch_t(gpx_ctx* h, const GemmArgs& a) {
+    static bool configured = false;
+    if (!configured) {
+        GPX_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<A_KM, B_KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured = true;
+    }
+    dim3 grid(a.N / BN, a.M / BM, a.batch > 0 ? a.batch : 1);
+    dgemm_dmma_kernel<A_KM, B_KM><<<grid, NTHREADS, SMEM_BYTES, h->stream>>>(a);
+    GPX_CHECK_LAUNCH(h);
+    return 0;
+}
+
+}  // namespace
+
+int gpx_gemm_launch(gpx_ctx* h, const GemmArgs& a) {
+    if (a.M <= 0 || a.N <= 0) return 0;
+    GPX_REQUIRE(a.M % BM == 0 && a.N % BN == 0 && a.K % BK == 0, 2);
+    GPX_REQUIRE(a.lda % 2 == 0 && a.ldb % 2 == 0 && a.ldc % 2 == 0, 3);
+    GPX_REQUIRE(((uintptr_t)a.A % 16) == 0 && ((uintptr_t)a.B % 16) == 0 && ((uintptr_t)a.C % 16) == 0, 4);
+    if (a.a_kmajor && a.b_kmajor) return launch_t<true, true>(h, a);
+    if (a.a_kmajor && !a.b_kmajor) return launch_t<true, false>(h, a);
+    if (!a.a_kmajor && a.b_kmajor) return launch_t<false, true>(h, a);
+    return launch_t<false, false>(h, a);
+}
+
+extern "C" int gpx_gemm(gpx_handle h, int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K, double alpha,
+                        const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc) {
+    GPX_REQUIRE(h != nullptr, 1);
+    GemmArgs a{};
+    a.A = A; a.B = B; a.C = C;
+    a.M = (int)M; a.N = (int)N; a.K = (int)K;
+    a.lda = lda; a.ldb = ldb; a.ldc = ldc;
+    a.alpha = alpha; a.beta = beta;
+    a.batch = 1;
+    a.a_kmajor = a_kmajor; a.b_kmajor = b_kmajor;
+    return gpx_gemm_launch(h, a);
+}

@@ -1,0 +1,361 @@
+// HBM-bound level-1/level-2 kernels: GEMV (N/T), blocked TRSV, dot / LML reductions, predictive moments,
+// small vector algebra for the Laplace loops.  
+#include "common.cuh"
+
+namespace {
+
+constexpr int LT = 128;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// y[r] = alpha * sum_c A[r][c] x[c] + beta * y[r]; one warp per row, 8 rows per CTA.
+__global__ void __launch_bounds__(256) gemv_n_kernel(int64_t m, int64_t n, double alpha, const double* __restrict__ A,
+                                                    int64_t lda, const double* __restrict__ x, double beta,
+                                                    double* __restrict__ y) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < m; r += (int64_t)gridDim.x * 8) {
+        const double* row = A + r * lda;
+        double s0 = 0.0, s1 = 0.0;
+        int64_t c = lane * 2;
+        if ((lda & 1) == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)x % 16) == 0) {
+            for (; c + 1 < n; c += 64) {
+                double2 a = *reinterpret_cast<const double2*>(row + c);
+                double2 xv = *reinterpret_cast<const double2*>(x + c);
+                s0 += a.x * xv.x;
+                s1 += a.y * xv.y;
+            }
+            if (c < n) s0 += row[c] * x[c];
+        } else {
+            for (c = lane; c < n; c += 32) s0 += row[c] * x[c];
+        }
+        double s = warp_sum(s0 + s1);
+        if (lane == 0) y[r] = alpha * s + (beta != 0.0 ? beta * y[r] : 0.0);
+    }
+}
+
+// partial[by][c] = sum_{r in row chunk by} A[r][c] x[r]; CTA = 128 columns x row chunk; 256 threads =
+// 2 row-lanes x 128 columns.
+__global__ void __launch_bounds__(256) gemv_t_partial_kernel(int64_t m, int64_t n, const double* __restrict__ A, int64_t lda,
+                                                            const double* __restrict__ x, double* __restrict__ partial,
+                                                            int64_t rows_per_cta) {
+    __shared__ double red[256];
+    const int cl = threadIdx.x & 127, rl = threadIdx.x >> 7;
+    const int64_t c = (int64_t)blockIdx.x * 128 + cl;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
+    int64_t r1 = r0 + rows_per_cta;
+    if (r1 > m) r1 = m;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (c < n) {
+        int64_t r = r0 + rl;
+        for (; r + 6 < r1; r += 8) {
+            s0 += A[r * lda + c] * x[r];
+            s1 += A[(r + 2) * lda + c] * x[r + 2];
+            s2 += A[(r + 4) * lda + c] * x[r + 4];
+            s3 += A[(r + 6) * lda + c] * x[r + 6];
+        }
+        for (; r < r1; r += 2) s0 += A[r * lda + c] * x[r];
+    }
+    red[threadIdx.x] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (rl == 0 && c < n) partial[(int64_t)blockIdx.y * n + c] = red[cl] + red[cl + 128];
+}
+
+__global__ void gemv_t_reduce_kernel(int64_t n, int nparts, double alpha, const double* __restrict__ partial, double beta,
+                                     double* __restrict__ y) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    double s = 0.0;
+    for (int p = 0; p < nparts; ++p) s += partial[(int64_t)p * n + c];
+    y[c] = alpha * s + (beta != 0.0 ? beta * y[c] : 0.0);
+}
+
+// x_blk <- Dinv x_blk (trans=0) or Dinv^T x_blk (trans=1) for one 128-leaf; one CTA of 128 threads.
+__global__ void __launch_bounds__(128) leaf_solve_kernel(const double* __restrict__ dinv, int trans, double* __restrict__ x) {
+    __shared__ double xs[LT];
+    const int t = threadIdx.x;
+    xs[t] = x[t];
+    __syncthreads();
+    double s = 0.0;
+    if (!trans) {
+        // row t of Dinv: warp-strided would be better coalesced, but 128x128 from L2 is latency-bound anyway
+        for (int k = 0; k <= t; ++k) s += dinv[t * LT + k] * xs[k];
+    } else {
+        for (int k = t; k < LT; ++k) s += dinv[k * LT + t] * xs[k];
+    }
+    x[t] = s;
+}
+
+__global__ void __launch_bounds__(256) dot_partial_kernel(int64_t n, const double* __restrict__ x, const double* __restrict__ y,
+                                                         double* __restrict__ partial) {
+    __shared__ double red[8];
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) s += x[i] * y[i];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        partial[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) logdiag_partial_kernel(int64_t n, const double* __restrict__ L, int64_t ldl,
+                                                             double* __restrict__ partial) {
+    __shared__ double red[8];
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) s += log(L[i * ldl + i]);
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        partial[blockIdx.x] = t;
+    }
+}
+
+// out[0] = sum partial[0..np)
+__global__ void finish_sum_kernel(int np, const double* __restrict__ partial, double* __restrict__ out) {
+    __shared__ double red[256];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < np; i += 256) s += partial[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = red[0];
+}
+
+// out3 = {-.5 ya - sl - n/2 log 2pi, ya, sl}
+__global__ void lml_finish_kernel(int np1, const double* p1, int np2, const double* p2, double n, double* out3) {
+    if (threadIdx.x == 0) {
+        double ya = 0.0, sl = 0.0;
+        for (int i = 0; i < np1; ++i) ya += p1[i];
+        for (int i = 0; i < np2; ++i) sl += p2[i];
+        out3[0] = -.5 * ya - sl - n / 2.0 * log(2 * 3.141592653589793238462643383279502884);
+        out3[1] = ya;
+        out3[2] = sl;
+    }
+}
+
+// mu[j] = sum_i Ks[i][j] alpha[i]; var[j] = kss[j] - sum_i V[i][j]^2  (column sums over n rows), partial pass
+__global__ void __launch_bounds__(256) moments_partial_kernel(int64_t n, int64_t m, int64_t ld, const double* __restrict__ Ks,
+                                                             const double* __restrict__ V, const double* __restrict__ alpha,
+                                                             double* __restrict__ pmu, double* __restrict__ pvv,
+                                                             int64_t rows_per_cta) {
+    __shared__ double r1[256], r2[256];
+    const int cl = threadIdx.x & 127, rl = threadIdx.x >> 7;
+    const int64_t c = (int64_t)blockIdx.x * 128 + cl;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
+    int64_t rend = r0 + rows_per_cta;
+    if (rend > n) rend = n;
+    double s = 0.0, q = 0.0;
+    if (c < m) {
+        for (int64_t r = r0 + rl; r < rend; r += 2) {
+            if (Ks) s += Ks[r * ld + c] * alpha[r];
+            if (V) {
+                double v = V[r * ld + c];
+                q += v * v;
+            }
+        }
+    }
+    r1[threadIdx.x] = s;
+    r2[threadIdx.x] = q;
+    __syncthreads();
+    if (rl == 0 && c < m) {
+        pmu[(int64_t)blockIdx.y * m + c] = r1[cl] + r1[cl + 128];
+        pvv[(int64_t)blockIdx.y * m + c] = r2[cl] + r2[cl + 128];
+    }
+}
+
+__global__ void moments_finish_kernel(int64_t m, int nparts, const double* __restrict__ pmu, const double* __restrict__ pvv,
+                                      const double* __restrict__ kss, double* __restrict__ mu, double* __restrict__ var) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m) return;
+    double s = 0.0, q = 0.0;
+    for (int p = 0; p < nparts; ++p) {
+        s += pmu[(int64_t)p * m + c];
+        q += pvv[(int64_t)p * m + c];
+    }
+    if (mu) mu[c] = s;
+    if (var) var[c] = kss[c] - q;
+}
+
+// element-wise vector algebra.  op codes (documented in INTEGRATION.md):
+//  0: out = a*x            1: out = x + a*y         2: out = x*y (+ z if z)     3: out = x - y*z
+//  4: out = a (fill)       5: out = x*y + z         6: out = (x - y)            7: out = x*y - z
+//  8: out = -log(1 + exp(-x))  (GP_binary...:63)     9: out = 1/(1+exp(-x)) (expit)   10: out = sqrt(x)
+__global__ void vec_op_kernel(int op, int64_t n, double a, const double* __restrict__ x, const double* __restrict__ y,
+                              const double* __restrict__ z, double* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double r = 0.0;
+    switch (op) {
+        case 0: r = a * x[i]; break;
+        case 1: r = x[i] + a * y[i]; break;
+        case 2: r = x[i] * y[i] + (z ? z[i] : 0.0); break;
+        case 3: r = x[i] - y[i] * z[i]; break;
+        case 4: r = a; break;
+        case 5: r = x[i] * y[i] + z[i]; break;
+        case 6: r = x[i] - y[i]; break;
+        case 7: r = x[i] * y[i] - z[i]; break;
+        case 8: r = -log(1.0 + exp(-x[i])); break;
+        case 9: r = x[i] >= 0.0 ? 1.0 / (1.0 + exp(-x[i])) : exp(x[i]) / (1.0 + exp(x[i])); break;
+        case 10: r = sqrt(x[i]); break;
+        default: r = 0.0;
+    }
+    out[i] = r;
+}
+
+__global__ void copy_strided_kernel(int64_t n, const double* __restrict__ src, int64_t ss, double* __restrict__ dst, int64_t ds) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i * ds] = src[i * ss];
+}
+
+int ensure_partial(gpx_ctx* h, size_t elems) {
+    if (h->partial_elems >= elems) return 0;
+    if (h->d_partial) cudaFree(h->d_partial);
+    h->d_partial = nullptr;
+    h->partial_elems = 0;
+    if (cudaMalloc(&h->d_partial, elems * sizeof(double)) != cudaSuccess) {
+        gpx_set_error("cudaMalloc of %zu reduction partials failed", elems);
+        return GPX_E_NOMEM;
+    }
+    h->partial_elems = elems;
+    return 0;
+}
+
+int gemv_impl(gpx_ctx* h, int trans, int64_t m, int64_t n, double alpha, const double* A, int64_t lda, const double* x,
+              double beta, double* y) {
+    if (m <= 0 || n <= 0) return 0;
+    if (!trans) {
+        int64_t blocks = (m + 7) / 8;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        gemv_n_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(m, n, alpha, A, lda, x, beta, y);
+        GPX_CHECK_LAUNCH(h);
+        return 0;
+    }
+    // y (n) = A^T x (m rows)
+    const int64_t colblocks = (n + 127) / 128;
+    int64_t nparts = (148 * 4 + colblocks - 1) / colblocks;
+    int64_t max_parts = (m + 63) / 64;
+    if (nparts > max_parts) nparts = max_parts;
+    if (nparts < 1) nparts = 1;
+    int64_t rows_per = (m + nparts - 1) / nparts;
+    rows_per = (rows_per + 1) & ~(int64_t)1;
+    nparts = (m + rows_per - 1) / rows_per;
+    GPX_TRY(ensure_partial(h, (size_t)(nparts * n)));
+    gemv_t_partial_kernel<<<dim3((unsigned)colblocks, (unsigned)nparts), 256, 0, h->stream>>>(m, n, A, lda, x, h->d_partial, rows_per);
+    GPX_CHECK_LAUNCH(h);
+    gemv_t_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(n, (int)nparts, alpha, h->d_partial, beta, y);
+    GPX_CHECK_LAUNCH(h);
+    return 0;
+}
+
+// recursive blocked TRSV on the factor (leaves use the 128x128 leaf inverses)
+int trsv_rec(gpx_ctx* h, const double* L, int64_t n, int64_t ldl, const double* dinv, int trans, double* x) {
+    if (n == LT) {
+        leaf_solve_kernel<<<1, 128, 0, h->stream>>>(dinv, trans, x);
+        GPX_CHECK_LAUNCH(h);
+        return 0;
+    }
+    const int64_t h1 = ((n / LT) / 2) * LT, h2 = n - h1;
+    const double* L21 = L + h1 * ldl;
+    const double* L22 = L21 + h1;
+    const double* dinv2 = dinv + (h1 / LT) * LT * LT;
+    if (!trans) {
+        GPX_TRY(trsv_rec(h, L, h1, ldl, dinv, 0, x));
+        GPX_TRY(gemv_impl(h, 0, h2, h1, -1.0, L21, ldl, x, 1.0, x + h1));
+        return trsv_rec(h, L22, h2, ldl, dinv2, 0, x + h1);
+    }
+    GPX_TRY(trsv_rec(h, L22, h2, ldl, dinv2, 1, x + h1));
+    GPX_TRY(gemv_impl(h, 1, h2, h1, -1.0, L21, ldl, x + h1, 1.0, x));
+    return trsv_rec(h, L, h1, ldl, dinv, 1, x);
+}
+
+}  // namespace
+
+extern "C" int gpx_gemv(gpx_handle h, int trans, int64_t m, int64_t n, double alpha, const double* A, int64_t lda,
+                        const double* x, double beta, double* y) {
+    GPX_REQUIRE(h != nullptr, 1);
+    return gemv_impl(h, trans, m, n, alpha, A, lda, x, beta, y);
+}
+
+extern "C" int gpx_trsv(gpx_handle h, const double* L, int64_t n, int64_t ldl, const double* dinv, int trans, double* x) {
+    GPX_REQUIRE(h != nullptr, 1);
+    GPX_REQUIRE(n > 0 && n % LT == 0, 3);
+    return trsv_rec(h, L, n, ldl, dinv, trans, x);
+}
+
+extern "C" int gpx_dot(gpx_handle h, int64_t n, const double* x, const double* y, double* out) {
+    GPX_REQUIRE(h != nullptr, 1);
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 592) blocks = 592;
+    if (blocks < 1) blocks = 1;
+    GPX_TRY(ensure_partial(h, 2048));
+    dot_partial_kernel<<<blocks, 256, 0, h->stream>>>(n, x, y, h->d_partial);
+    GPX_CHECK_LAUNCH(h);
+    finish_sum_kernel<<<1, 256, 0, h->stream>>>(blocks, h->d_partial, out);
+    GPX_CHECK_LAUNCH(h);
+    return 0;
+}
+
+extern "C" int gpx_lml(gpx_handle h, const double* L, int64_t n, int64_t ldl, const double* y, const double* alpha,
+                       double* out3) {
+    GPX_REQUIRE(h != nullptr, 1);
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 592) blocks = 592;
+    GPX_TRY(ensure_partial(h, 2048));
+    dot_partial_kernel<<<blocks, 256, 0, h->stream>>>(n, y, alpha, h->d_partial);
+    GPX_CHECK_LAUNCH(h);
+    logdiag_partial_kernel<<<blocks, 256, 0, h->stream>>>(n, L, ldl, h->d_partial + 1024);
+    GPX_CHECK_LAUNCH(h);
+    lml_finish_kernel<<<1, 32, 0, h->stream>>>(blocks, h->d_partial, blocks, h->d_partial + 1024, (double)n, out3);
+    GPX_CHECK_LAUNCH(h);
+    return 0;
+}
+
+extern "C" int gpx_predict_moments(gpx_handle h, const double* Ks, const double* V, int64_t n, int64_t m, int64_t ld,
+                                   const double* alpha, const double* kss_diag, double* mu, double* var) {
+    GPX_REQUIRE(h != nullptr, 1);
+    const int64_t colblocks = (m + 127) / 128;
+    int64_t nparts = (148 * 4 + colblocks - 1) / colblocks;
+    int64_t max_parts = (n + 63) / 64;
+    if (nparts > max_parts) nparts = max_parts;
+    if (nparts < 1) nparts = 1;
+    int64_t rows_per = (n + nparts - 1) / nparts;
+    rows_per = (rows_per + 1) & ~(int64_t)1;
+    nparts = (n + rows_per - 1) / rows_per;
+    GPX_TRY(ensure_partial(h, (size_t)(2 * nparts * m)));
+    double* pmu = h->d_partial;
+    double* pvv = h->d_partial + nparts * m;
+    moments_partial_kernel<<<dim3((unsigned)colblocks, (unsigned)nparts), 256, 0, h->stream>>>(n, m, ld, Ks, V, alpha, pmu, pvv, rows_per);
+    GPX_CHECK_LAUNCH(h);
+    moments_finish_kernel<<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(m, (int)nparts, pmu, pvv, kss_diag, mu, var);
+    GPX_CHECK_LAUNCH(h);
+    return 0;
+}
+
+extern "C" int gpx_vec_op(gpx_handle h, int op, int64_t n, double a, const double* x, const double* y, const double* z,
+                          double* out) {
+    GPX_REQUIRE(h != nullptr, 1);
+    if (n <= 0) return 0;
+    vec_op_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(op, n, a, x, y, z, out);
+    GPX_CHECK_LAUNCH(h);
+    return 0;
+}
+
+extern "C" int gpx_copy_strided(gpx_handle h, int64_t n, const double* src, int64_t src_stride, double* dst, int64_t dst_stride) {
+    GPX_REQUIRE(h != nullptr, 1);
+    if (n <= 0) return 0;
+    copy_strided_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(n, src, src_stride, dst, dst_stride);
+    GPX_CHECK_LAUNCH(h);
+    return 0;
+}

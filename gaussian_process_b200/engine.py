@@ -1,0 +1,316 @@
+"""Host-side engine: thin, typed wrappers over the libgpx C ABI.
+
+torch is used only as the device-memory allocator / stream provider (``tensor.data_ptr()`` crosses
+the ABI); every floating-point operation of the GP path runs in libgpx's sm_100a kernels.  There is
+no CPU fallback -- constructing an :class:`Engine` without the library or without a B200 raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import COV_CO2, COV_LIN, COV_LOWER, COV_PER, COV_SAME_X, COV_SE, GPX_TILE, GpxError, check
+
+_KIND_NTHETA = {COV_SE: 2, COV_LIN: 1, COV_PER: 2, COV_CO2: 11}
+
+
+def padded(n: int) -> int:
+    return ((int(n) + GPX_TILE - 1) // GPX_TILE) * GPX_TILE
+
+
+def _theta_array(theta: Sequence[float]):
+    t = np.ascontiguousarray(np.asarray(theta, dtype=np.float64).reshape(-1))
+    return t, t.ctypes.data_as(ctypes.c_void_p)
+
+
+@dataclass
+class GPFit:
+    """Device-resident state of one exact-GP fit (K + sI = L L^T)."""
+    kind: int
+    theta: np.ndarray
+    s: float
+    n: int
+    npad: int
+    X: "object"          # torch (n, D) device
+    y: "object"          # torch (n,) device
+    L: "object"          # torch (npad, npad) device: lower factor (upper zero); L^-1 after fit_grad
+    dinv: "object"       # torch (npad/128, 128, 128): inverses of L's diagonal blocks
+    alpha: "object"      # torch (npad,)
+    lml: float
+    y_alpha: float
+    sum_log_diag: float
+    grad: Optional[np.ndarray] = None
+    Kinv: "object" = None
+    L_is_inverse: bool = False
+
+
+class Engine:
+    """One libgpx handle bound to one CUDA device."""
+
+    def __init__(self, device: int = 0):
+        import torch
+
+        self.torch = torch
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise GpxError("no CUDA device visible: the gpx engine has no CPU fallback")
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        h = ctypes.c_void_p()
+        check(self.lib.gpx_create(device, ctypes.byref(h)), "gpx_create")
+        self.h = h
+        self._sync_stream()
+
+    # ------------------------------------------------------------------ plumbing
+    def _sync_stream(self):
+        s = self.torch.cuda.current_stream(self.device).cuda_stream
+        check(self.lib.gpx_set_stream(self.h, ctypes.c_void_p(s)), "gpx_set_stream")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gpx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def launches(self) -> int:
+        return int(self.lib.gpx_launch_count(self.h))
+
+    def synchronize(self):
+        check(self.lib.gpx_synchronize(self.h), "gpx_synchronize")
+
+    def empty(self, *shape):
+        return self.torch.empty(*shape, dtype=self.torch.float64, device=self.device)
+
+    def zeros(self, *shape):
+        return self.torch.zeros(*shape, dtype=self.torch.float64, device=self.device)
+
+    def to_device(self, a, pinned: bool = False):
+        """NumPy -> device tensor (float64, C-contiguous)."""
+        torch = self.torch
+        if isinstance(a, torch.Tensor):
+            return a.to(device=self.device, dtype=torch.float64).contiguous()
+        arr = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+        t = torch.from_numpy(arr)
+        if pinned:
+            t = t.pin_memory()
+        return t.to(self.device, non_blocking=pinned)
+
+    def to_host(self, t) -> np.ndarray:
+        return t.detach().cpu().numpy()
+
+    @staticmethod
+    def _p(t):
+        return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+    # ------------------------------------------------------------------ A1-A3 covariance
+    def cov(self, kind: int, X1, X2, theta, diag_add: float = 0.0, same_x: bool = False, lower: bool = False,
+            out=None, with_grad: bool = False):
+        """K (padded) = k(X1, X2; theta) [+ diag_add I].  Returns K or (K, dK[ntheta]) device tensors."""
+        self._sync_stream()
+        n1, D = X1.shape
+        n2 = X2.shape[0]
+        n1p, n2p = padded(n1), padded(n2)
+        K = out if out is not None else self.empty(n1p, n2p)
+        th, thp = _theta_array(theta)
+        flags = (COV_SAME_X if same_x else 0) | (COV_LOWER if lower else 0)
+        dK = self.empty(len(th), n1p, n2p) if with_grad else None
+        check(self.lib.gpx_cov_build(self.h, kind, self._p(X1), n1, self._p(X2), n2, D, thp, len(th), float(diag_add), flags,
+                                     self._p(K), n1p, n2p, K.stride(0), self._p(dK), n1p * n2p), "gpx_cov_build")
+        return (K, dK) if with_grad else K
+
+    # ------------------------------------------------------------------ A4/A5 dense linear algebra
+    def potrf(self, A):
+        """In-place lower Cholesky of a padded square tensor; returns the leaf-inverse buffer."""
+        self._sync_stream()
+        n = A.shape[0]
+        dinv = self.empty(n // GPX_TILE, GPX_TILE, GPX_TILE)
+        check(self.lib.gpx_potrf(self.h, self._p(A), n, A.stride(0), self._p(dinv)), "gpx_potrf")
+        return dinv
+
+    def trsv(self, L, dinv, x, trans: bool = False):
+        self._sync_stream()
+        check(self.lib.gpx_trsv(self.h, self._p(L), L.shape[0], L.stride(0), self._p(dinv), int(trans), self._p(x)), "gpx_trsv")
+        return x
+
+    def trsm(self, L, dinv, B, trans: bool = False):
+        self._sync_stream()
+        check(self.lib.gpx_trsm(self.h, self._p(L), L.shape[0], L.stride(0), self._p(dinv), int(trans), self._p(B),
+                                B.shape[1], B.stride(0)), "gpx_trsm")
+        return B
+
+    def potrs_vec(self, L, dinv, x):
+        """x <- (L L^T)^-1 x."""
+        self.trsv(L, dinv, x, False)
+        return self.trsv(L, dinv, x, True)
+
+    def trtri(self, L, dinv, work=None):
+        self._sync_stream()
+        n = L.shape[0]
+        if work is None and n > GPX_TILE:
+            work = self.empty((n // 2 + GPX_TILE) * (n // 2 + GPX_TILE))
+        check(self.lib.gpx_trtri(self.h, self._p(L), n, L.stride(0), self._p(dinv), self._p(work)), "gpx_trtri")
+        return L
+
+    def lauum(self, Linv, out=None):
+        self._sync_stream()
+        n = Linv.shape[0]
+        if out is None:
+            out = self.zeros(n, n)
+        check(self.lib.gpx_lauum(self.h, self._p(Linv), n, Linv.stride(0), self._p(out), out.stride(0)), "gpx_lauum")
+        return out
+
+    def gemm(self, A, B, C, a_kmajor: bool, b_kmajor: bool, M: int, N: int, K: int, alpha=1.0, beta=0.0):
+        self._sync_stream()
+        check(self.lib.gpx_gemm(self.h, int(a_kmajor), int(b_kmajor), M, N, K, float(alpha), self._p(A), A.stride(0),
+                                self._p(B), B.stride(0), float(beta), self._p(C), C.stride(0)), "gpx_gemm")
+        return C
+
+    def gemv(self, A, x, y, trans: bool = False, alpha=1.0, beta=0.0, m=None, n=None):
+        self._sync_stream()
+        m = A.shape[0] if m is None else m
+        n = A.shape[1] if n is None else n
+        check(self.lib.gpx_gemv(self.h, int(trans), m, n, float(alpha), self._p(A), A.stride(0), self._p(x), float(beta),
+                                self._p(y)), "gpx_gemv")
+        return y
+
+    def symv_lower(self, S, x, y, n=None):
+        self._sync_stream()
+        n = S.shape[0] if n is None else n
+        check(self.lib.gpx_symv_lower(self.h, n, self._p(S), S.stride(0), self._p(x), self._p(y)), "gpx_symv_lower")
+        return y
+
+    def vec_op(self, op: int, n: int, out, a=0.0, x=None, y=None, z=None):
+        self._sync_stream()
+        check(self.lib.gpx_vec_op(self.h, op, n, float(a), self._p(x), self._p(y), self._p(z), self._p(out)), "gpx_vec_op")
+        return out
+
+    def dot(self, x, y, n=None) -> float:
+        self._sync_stream()
+        n = x.numel() if n is None else n
+        out = self.empty(1)
+        check(self.lib.gpx_dot(self.h, n, self._p(x), self._p(y), self._p(out)), "gpx_dot")
+        return float(out.item())
+
+    def diag(self, A, n=None):
+        self._sync_stream()
+        n = A.shape[0] if n is None else n
+        out = self.empty(n)
+        check(self.lib.gpx_copy_strided(self.h, n, self._p(A), A.stride(0) + 1, self._p(out), 1), "gpx_copy_strided")
+        return out
+
+    # ------------------------------------------------------------------ fit / LML / gradient
+    def fit(self, kind: int, X, y, theta, s: float, with_grad: bool = False) -> GPFit:
+        """K = cov(X,X;theta) + s I = L L^T, alpha = K^-1 y, LML [and dLML/dtheta]."""
+        self._sync_stream()
+        Xd = self.to_device(X)
+        yd = self.to_device(np.asarray(y).reshape(-1) if not hasattr(y, "data_ptr") else y.reshape(-1))
+        n, D = Xd.shape
+        npad = padded(n)
+        th, thp = _theta_array(theta)
+        A = self.empty(npad, npad)
+        dinv = self.empty(npad // GPX_TILE, GPX_TILE, GPX_TILE)
+        alpha = self.empty(npad)
+        out = self.empty(3 + 11)
+        Kinv = None
+        if with_grad:
+            Kinv = self.empty(npad, npad)
+            st = self.lib.gpx_gp_fit_grad(self.h, kind, self._p(Xd), n, D, thp, len(th), float(s), self._p(yd), self._p(A),
+                                          npad, A.stride(0), self._p(dinv), self._p(Kinv), self._p(alpha), self._p(out),
+                                          ctypes.c_void_p(out.data_ptr() + 24))
+        else:
+            st = self.lib.gpx_gp_fit(self.h, kind, self._p(Xd), n, D, thp, len(th), float(s), self._p(yd), self._p(A), npad,
+                                     A.stride(0), self._p(dinv), self._p(alpha), self._p(out))
+        check(st, "gpx_gp_fit")
+        o = self.to_host(out)
+        return GPFit(kind, th, float(s), n, npad, Xd, yd, A, dinv, alpha, float(o[0]), float(o[1]), float(o[2]),
+                     grad=o[3:3 + len(th)].copy() if with_grad else None, Kinv=Kinv, L_is_inverse=with_grad)
+
+    def lml_grad(self, kind: int, Xd, theta, Kinv, alpha, n=None) -> np.ndarray:
+        """.5 sum_ik (alpha_i alpha_k - Kinv_ik) dK_ik/dtheta_j for every theta_j (fused kernel) -> host array."""
+        self._sync_stream()
+        n = Xd.shape[0] if n is None else n
+        th, thp = _theta_array(theta)
+        grad = self.empty(len(th))
+        check(self.lib.gpx_lml_grad(self.h, kind, self._p(Xd), n, Xd.shape[1], thp, len(th), self._p(Kinv), Kinv.stride(0),
+                                    self._p(alpha), self._p(grad)), "gpx_lml_grad")
+        return self.to_host(grad)
+
+    def inverse_from_factor(self, fit: "GPFit"):
+        """K_y^-1 (lower triangle valid) from a fit: L <- L^-1 in place, then Linv^T Linv (tune...:144)."""
+        work = self.empty(fit.npad, fit.npad)
+        self.trtri(fit.L, fit.dinv, work)
+        fit.L_is_inverse = True
+        fit.Kinv = self.lauum(fit.L, work)
+        return fit.Kinv
+
+    # ------------------------------------------------------------------ A6 prediction
+    def predict(self, fit: GPFit, Xs, want_v: bool = False, kss_diag=None):
+        """mu = K_s^T alpha, var = diag(K_ss) - colsum((L^-1 K_s)^2)  (GP_regression.py:143-147).
+
+        Returns (mu, var, V or None) as device tensors of the true test size (V is padded)."""
+        self._sync_stream()
+        if fit.L_is_inverse:
+            raise GpxError("predict() needs the factor L; this fit holds L^-1 (fit_grad overwrote it)")
+        Xsd = self.to_device(Xs)
+        m = Xsd.shape[0]
+        Ks = self.cov(fit.kind, fit.X, Xsd, fit.theta)                      # (npad, mpad)
+        mu = self.empty(m)
+        var = self.empty(m)
+        lib = self.lib
+        check(lib.gpx_predict_moments(self.h, self._p(Ks), None, fit.n, m, Ks.stride(0), self._p(fit.alpha), None,
+                                      self._p(mu), None), "gpx_predict_moments(mu)")
+        self.trsm(fit.L, fit.dinv, Ks, trans=False)                          # Ks <- V = L^-1 K_s
+        if kss_diag is None:
+            Kss = self.cov(fit.kind, Xsd, Xsd, fit.theta, same_x=True)
+            kss_diag = self.diag(Kss, m)
+        check(lib.gpx_predict_moments(self.h, None, self._p(Ks), fit.n, m, Ks.stride(0), None, self._p(kss_diag), None,
+                                      self._p(var)), "gpx_predict_moments(var)")
+        return mu, var, (Ks if want_v else None)
+
+    def posterior_sample_factor(self, kind: int, theta, Xs_dev, V, jitter: float = 1e-6):
+        """L_ = chol(K_ss + jitter I - V^T V)  (GP_regression.py:154).  Returns (L_ padded, K_ss diag)."""
+        m = Xs_dev.shape[0]
+        Kss = self.cov(kind, Xs_dev, Xs_dev, theta, same_x=True)
+        kss_diag = self.diag(Kss, m)
+        # add jitter on the true diagonal only: rebuild with diag_add (padding stays identity)
+        C = self.cov(kind, Xs_dev, Xs_dev, theta, diag_add=jitter, same_x=True)
+        mp = C.shape[0]
+        self.gemm(V, V, C, a_kmajor=False, b_kmajor=False, M=mp, N=mp, K=V.shape[0], alpha=-1.0, beta=1.0)
+        self.potrf(C)
+        return C, kss_diag
+
+    def tri_times(self, Lfac, Z_host: np.ndarray, n: int) -> np.ndarray:
+        """(L_ z) for host normals z (n, num_fun): GEMM on device, result on host."""
+        mp = Lfac.shape[0]
+        nf = Z_host.shape[1]
+        Zp = self.zeros(mp, padded(nf))
+        Zp[:n, :nf] = self.to_device(Z_host)
+        out = self.empty(mp, padded(nf))
+        self.gemm(Lfac, Zp, out, a_kmajor=True, b_kmajor=False, M=mp, N=padded(nf), K=mp)
+        return self.to_host(out[:n, :nf])
+
+    # ------------------------------------------------------------------ measurement
+    def fp64_peak(self, dmma: bool = True, iters: int = 4096):
+        tf = ctypes.c_double()
+        ms = ctypes.c_double()
+        check(self.lib.gpx_bench_fp64_peak(self.h, int(dmma), iters, ctypes.byref(tf), ctypes.byref(ms)), "gpx_bench_fp64_peak")
+        return tf.value, ms.value
+
+
+_engines = {}
+
+
+def get_engine(device: int = 0) -> Engine:
+    """Process-wide engine per device (handles are cheap but workspaces are not)."""
+    if device not in _engines:
+        _engines[device] = Engine(device)
+    return _engines[device]

@@ -1,0 +1,187 @@
+/*
+ * gpx.h -- C ABI of libgpx.so, the B200-native (sm_100a) exact-Gaussian-process engine.
+ *
+ * Drop-in boundary: the reference (happyjin/Gaussian_process) has no FFI; its
+ * boundary is the set of module-level NumPy functions its five scripts call.  libgpx replaces the
+ * linear algebra *inside* those functions.  Every entry point below names the reference lines whose
+ * arithmetic it replaces.  The Python host side (gaussian_process_b200/*.py, same module / function
+ * names as the reference) binds these with ctypes; see INTEGRATION.md for the stub a maintainer of
+ * the reference would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types, no exceptions cross the boundary.
+ *   - all matrices are IEEE float64, ROW-MAJOR, leading dimension `ld` in elements.
+ *   - "device" entry points (gpx_*) take DEVICE pointers (e.g. torch tensor .data_ptr()) and run on
+ *     the handle's stream; "host" entry points (gpx_host_*) take HOST pointers, do the H2D/D2H
+ *     copies themselves and synchronise before returning.
+ *   - return value: 0 = ok; >0 = LAPACK-style index (1-based) of the first non-positive pivot
+ *     (the Python layer raises numpy.linalg.LinAlgError, as np.linalg.cholesky does); <0 = error
+ *     (-k = bad argument k, or GPX_E_*), text via gpx_last_error().
+ *   - dense kernels run on padded tiles: dimensions given to the device-level linear-algebra calls
+ *     must be multiples of GPX_TILE (128).  gpx_cov_build pads for you (identity on the padded
+ *     diagonal, zeros elsewhere) so a padded factorisation equals the unpadded one.
+ */
+#ifndef GPX_H
+#define GPX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPX_VERSION 100
+#define GPX_TILE 128
+
+#define GPX_E_CUDA   (-100)   /* a CUDA runtime call failed            */
+#define GPX_E_ARG    (-101)   /* generic bad argument                  */
+#define GPX_E_NOMEM  (-102)   /* workspace allocation failed           */
+#define GPX_E_NCCL   (-103)   /* NCCL not initialised / call failed    */
+
+typedef struct gpx_ctx* gpx_handle;
+
+/* covariance families (theta layout in brackets) */
+enum gpx_cov_kind {
+    GPX_COV_SE   = 0,  /* [sigma, l]   sigma^2 exp(-.5 d / l^2)            GP_regression.py:8-19      */
+    GPX_COV_LIN  = 1,  /* [c]          (a-c).(b-c)                          GP_regression.py:22-33     */
+    GPX_COV_PER  = 2,  /* [p, l]       exp(-2 sin^2(pi r/p)/l^2)            GP_regression.py:36-50     */
+    GPX_COV_CO2  = 3   /* [theta1..11] SE + SE*periodic + RQ + SE + delta   CO2_example.py:9-94        */
+};
+
+/* flags for gpx_cov_build */
+#define GPX_COV_SAME_X   1   /* X1 is X2: square block; theta11^2 delta (CO2) and `diag_add` go on the diagonal */
+#define GPX_COV_LOWER    2   /* only tiles on/below the diagonal are computed; strictly-upper tiles are zeroed  */
+
+/* ---- library / handle ------------------------------------------------------------------- */
+int         gpx_version(void);
+const char* gpx_last_error(void);
+int         gpx_create(int device, gpx_handle* out);
+int         gpx_destroy(gpx_handle h);
+int         gpx_set_stream(gpx_handle h, void* cuda_stream);      /* cudaStream_t; NULL = default */
+int         gpx_synchronize(gpx_handle h);
+int64_t     gpx_padded_dim(int64_t n);                             /* round up to GPX_TILE */
+/* number of kernels launched by this handle since creation (bench.py's gpu_launches) */
+int64_t     gpx_launch_count(gpx_handle h);
+
+/* ---- A1-A3: fused covariance builder ----------------------------------------------------
+ * K[i,j] = k(X1[i,:], X2[j,:]; theta) for i<n1, j<n2; rows/cols up to (n1p,n2p) are padding:
+ * zero, except K[i,i] = 1 for i >= n1 when GPX_COV_SAME_X (identity padding).  `diag_add` (the
+ * reference's `+ s*np.eye(N)`, e.g. GP_regression.py:138) is added on the true diagonal when
+ * SAME_X.  If dK != NULL, the ntheta derivative matrices dK/dtheta_j (SURVEY Appendix C;
+ * tune_hyperparms_regression.py:48,54) are written in the same pass to dK + j*dk_stride.
+ * Replaces GP_regression.py:18-19,32,48-49 and CO2_example.py:79-93. */
+int gpx_cov_build(gpx_handle h, int kind, const double* X1, int64_t n1, const double* X2, int64_t n2,
+                  int D, const double* theta_host, int ntheta, double diag_add, int flags,
+                  double* K, int64_t n1p, int64_t n2p, int64_t ldk, double* dK, int64_t dk_stride);
+
+/* ---- A4: Cholesky (np.linalg.cholesky call sites) ------------------------
+ * In-place lower Cholesky of the n x n (n % 128 == 0) matrix A; on return the lower triangle holds
+ * L and the strict upper triangle is zero (NumPy convention).  Blocked recursive right-looking:
+ * 128x128 leaf factor (warp-shuffle/shared-memory kernel) + FP64 DMMA (mma.sync m8n8k4) TRSM/SYRK.
+ * `dinv` (n/128 tiles of 128x128, device) receives the inverses of the diagonal blocks of L; they
+ * are required by the solve / inverse routines below. */
+int gpx_potrf(gpx_handle h, double* A, int64_t n, int64_t lda, double* dinv);
+
+/* ---- A5: triangular solves (np.linalg.solve(L,.) / inv(L) call sites, row A5) -------------- */
+/* x <- L^-1 x (trans=0) or L^-T x (trans=1), one right-hand side, HBM-bound blocked TRSV. */
+int gpx_trsv(gpx_handle h, const double* L, int64_t n, int64_t ldl, const double* dinv, int trans, double* x);
+/* B <- L^-1 B (trans=0) or L^-T B (trans=1); B is n x nrhs row-major, nrhs % 128 == 0. */
+int gpx_trsm(gpx_handle h, const double* L, int64_t n, int64_t ldl, const double* dinv, int trans,
+             double* B, int64_t nrhs, int64_t ldb);
+/* In-place inverse of the lower-triangular factor: L <- L^-1 (np.linalg.inv(L), tune...:144).
+ * `work` must hold n*n/4 doubles. */
+int gpx_trtri(gpx_handle h, double* L, int64_t n, int64_t ldl, const double* dinv, double* work);
+/* out(lower) <- Linv^T Linv = (L L^T)^-1   (np.dot(inv(L.T), inv(L)), tune...:144); out != Linv. */
+int gpx_lauum(gpx_handle h, const double* Linv, int64_t n, int64_t ldl, double* out, int64_t ldo);
+
+/* general FP64 DMMA GEMM: C = alpha * op(A) op(B) + beta * C.  a_kmajor: A stored [M][K] (1) or
+ * [K][M] (0); b_kmajor: B stored [N][K] (1) or [K][N] (0).  M,N % 128 == 0, K % 16 == 0. */
+int gpx_gemm(gpx_handle h, int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K, double alpha,
+             const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc);
+/* y = alpha * op(A) x + beta * y for row-major A (m x n); trans=1 uses A^T. */
+int gpx_gemv(gpx_handle h, int trans, int64_t m, int64_t n, double alpha, const double* A, int64_t lda,
+             const double* x, double beta, double* y);
+
+/* ---- A6/A7: predictive moments and log marginal likelihood --------------------------------
+ * out[0] = -.5 y.alpha - sum_i log L_ii - n/2 log(2 pi)   (tune...:141,312; CO2...:148)
+ * out[1] = y.alpha, out[2] = sum log L_ii.   n = true (unpadded) size. */
+int gpx_lml(gpx_handle h, const double* L, int64_t n, int64_t ldl, const double* y, const double* alpha, double* out3);
+/* mu[j] = sum_i Ks[i,j] alpha[i]; var[j] = kss_diag[j] - sum_i V[i,j]^2 (GP_regression.py:143-147). */
+int gpx_predict_moments(gpx_handle h, const double* Ks, const double* V, int64_t n, int64_t m, int64_t ld,
+                        const double* alpha, const double* kss_diag, double* mu, double* var);
+
+/* ---- A8: fused LML gradient -----------------------------------------------------------------
+ * grad[j] = .5 * sum_ik (alpha_i alpha_k - Kinv_ik) dK_ik/dtheta_j with dK recomputed on the fly
+ * from X (never materialised); Kinv is read once (lower triangle, symmetric weights).
+ * Replaces tune_hyperparms_regression.py:43-57 (N x N x N GEMM + trace).  grad is DEVICE memory. */
+int gpx_lml_grad(gpx_handle h, int kind, const double* X, int64_t n, int D, const double* theta_host, int ntheta,
+                 const double* Kinv, int64_t ldk, const double* alpha, double* grad);
+
+/* ---- fused drivers used by the Python drop-in modules and bench.py -------------------------
+ * gp_fit: K = cov(X,X;theta) + s I  ->  L (in A, padded np x np), dinv, alpha = K^-1 y (np doubles, y is
+ * padded with zeros by the callee), out3 = {lml, y.alpha, sum log L_ii}.  Follows
+ * tune_hyperparms_regression.py:306-312 / CO2_example.py:142-148. */
+int gpx_gp_fit(gpx_handle h, int kind, const double* X, int64_t n, int D, const double* theta_host, int ntheta,
+               double s, const double* y, double* A, int64_t np_, int64_t lda, double* dinv,
+               double* alpha, double* out3);
+/* gp_fit + K^-1 (trtri + lauum into Kinv) + fused gradient; `A` ends up holding L^-1.
+ * Follows tune_hyperparms_regression.py:123-145.  Kinv: np x np doubles (ld = lda). */
+int gpx_gp_fit_grad(gpx_handle h, int kind, const double* X, int64_t n, int D, const double* theta_host, int ntheta,
+                    double s, const double* y, double* A, int64_t np_, int64_t lda, double* dinv,
+                    double* Kinv, double* alpha, double* out3, double* grad);
+
+/* ---- A10/A11: Laplace building blocks --------------------------------------------------------*/
+/* binary (GP_binary_classification.py:48-83,104-105): mode 0 = reference-faithful gradient
+ * t - sigmoid(y f), mode 1 = textbook t - sigmoid(f); w = sigmoid(f)(1-sigmoid(f)); sw = sqrt(w). */
+int gpx_logistic_terms(gpx_handle h, int mode, int64_t n, const double* y, const double* f,
+                       double* grad, double* w, double* sw);
+/* B = I + diag(sw) K diag(sw)  (GP_binary...:107, GP_multi...:93), np x np padded, identity padding. */
+int gpx_build_B(gpx_handle h, const double* K, const double* sw, int64_t n, int64_t np_, int64_t ld, double* B);
+/* softmax over classes: f, pi are class-major (C, stride) (GP_multi...:26-63). */
+int gpx_softmax_classes(gpx_handle h, int C, int64_t n, int64_t stride, const double* f, double* pi);
+/* Reference-faithful multiclass pieces (GP_multi...:150-157): the reference's pi_matrix is POINT-major
+ * (row a = i*C + c) while D = diag(pi_vector) is CLASS-major (index c*stride + i, stride = literal 60).
+ * out = Kinv + c_diag*I + diag(pi_vec) - Pi Pi^T on the padded np x np buffer (identity padding). */
+int gpx_multi_ref_hessian(gpx_handle h, int C, int64_t n, int64_t stride, const double* Kinv, int64_t ld,
+                          const double* pi_vec, double c_diag, int64_t np_, double* out);
+/* out = (D - Pi Pi^T) f with the same conventions (GP_multi...:157). */
+int gpx_multi_ref_wf(gpx_handle h, int C, int64_t n, int64_t stride, const double* pi_vec, const double* f, double* out);
+/* Textbook Alg. 3.3 (class-major Pi): b = (D - Pi Pi^T) f + y - pi  (GP_multi...:113 with b = W f + y - pi). */
+int gpx_multi_b(gpx_handle h, int C, int64_t n, const double* pi, const double* f, const double* y, double* b);
+/* E(lower tiles) (+)= diag(sd) X diag(sd)   (E_c of GP_multi...:95 and its sum :101). */
+int gpx_scale_sym_acc(gpx_handle h, const double* X, const double* sd, int64_t n, int64_t np_, int64_t ld,
+                      int accumulate, double* E);
+/* M[i,:] *= s[i] (W^1/2 k_* of GP_binary...:151). */
+int gpx_scale_rows(gpx_handle h, int64_t rows, int64_t cols, int64_t ld, const double* s, double* M);
+/* copy the strictly-lower triangle of the n x n matrix A into its upper triangle. */
+int gpx_symmetrize(gpx_handle h, int64_t n, double* A, int64_t ld);
+/* y = S x for a symmetric S stored in its lower triangle. */
+int gpx_symv_lower(gpx_handle h, int64_t n, const double* S, int64_t ld, const double* x, double* y);
+/* small vector algebra on device (n doubles): see gpx_vec_op codes in vec.cu */
+int gpx_vec_op(gpx_handle h, int op, int64_t n, double a, const double* x, const double* y, const double* z, double* out);
+/* dst[i*dst_stride] = src[i*src_stride], i < n (e.g. diagonal extraction with src_stride = ld+1) */
+int gpx_copy_strided(gpx_handle h, int64_t n, const double* src, int64_t src_stride, double* dst, int64_t dst_stride);
+/* out[0] = sum_i x_i*y_i (y may equal x) -- device scalar */
+int gpx_dot(gpx_handle h, int64_t n, const double* x, const double* y, double* out);
+
+/* ---- measurement helpers --------------------------------------------------------------------
+ * register-resident DMMA.8x8x4 / DFMA issue-rate microbenchmarks -> measured FP64 peaks (TFLOP/s). */
+int gpx_bench_fp64_peak(gpx_handle h, int use_dmma, int iters, double* tflops_out, double* ms_out);
+
+/* ---- multi-GPU (one process per GPU; NCCL communicator owned by the handle) -----------------*/
+int gpx_nccl_unique_id(void* id128);                                  /* rank 0: fills 128 bytes */
+int gpx_nccl_init(gpx_handle h, const void* id128, int rank, int world);
+/* 1-D block-cyclic (column blocks of `nb`) right-looking Cholesky with NCCL panel broadcast.
+ * Aloc: n x (local columns) row-major, local column block q holds global block q*world+rank. */
+int gpx_potrf_mg(gpx_handle h, double* Aloc, int64_t n, int64_t ldl, int64_t nb, double* panel, double* dinv);
+
+/* ---- host-buffer drop-in calls (HOST pointers; copies inside; synchronous) ------------------*/
+/* LML (+ optional gradient wrt all theta when grad_host != NULL) of y ~ GP(0, cov + s I). */
+int gpx_host_lml(gpx_handle h, int kind, const double* X, int64_t n, int D, const double* theta, int ntheta,
+                 double s, const double* y, double* lml_out, double* grad_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPX_H */

@@ -1,0 +1,61 @@
+"""CPU checks of the boundary: libgpx.so loads, exports every symbol include/gpx.h declares, and the
+product path fails loudly (no CPU fallback) when no GPU is present."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from gaussian_process_b200 import _lib
+
+
+def test_header_parses_and_library_exports_every_symbol():
+    protos = _lib.parse_header()
+    assert len(protos) >= 35
+    for must in ("gpx_create", "gpx_cov_build", "gpx_potrf", "gpx_trsv", "gpx_trsm", "gpx_trtri", "gpx_lauum", "gpx_gemm",
+                 "gpx_lml", "gpx_lml_grad", "gpx_gp_fit", "gpx_gp_fit_grad", "gpx_host_lml", "gpx_logistic_terms",
+                 "gpx_build_B", "gpx_softmax_classes", "gpx_potrf_mg", "gpx_nccl_init"):
+        assert must in protos, must
+    if not os.path.isfile(_lib.LIB_PATH):
+        pytest.skip("libgpx.so not built (run __graft_entry__.build())")
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in protos:
+        assert hasattr(lib, name), "libgpx.so does not export %s" % name
+
+
+def test_version_and_padding_without_gpu():
+    if not os.path.isfile(_lib.LIB_PATH):
+        pytest.skip("libgpx.so not built")
+    lib = _lib.load()
+    assert lib.gpx_version() == 100
+    assert lib.gpx_padded_dim(1) == 128 and lib.gpx_padded_dim(128) == 128 and lib.gpx_padded_dim(129) == 256
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from gaussian_process_b200 import GpxError, GP_regression as G
+    with pytest.raises(GpxError):
+        G.RBF_kernel(np.zeros((3, 1)), np.zeros((3, 1)), 1, 1)
+    if os.path.isfile(_lib.LIB_PATH):
+        lib = _lib.load()
+        h = ctypes.c_void_p()
+        assert lib.gpx_create(0, ctypes.byref(h)) < 0
+        assert b"no CPU fallback" in lib.gpx_last_error() or b"CUDA" in lib.gpx_last_error()
+
+
+def test_status_mapping():
+    with pytest.raises(np.linalg.LinAlgError):
+        _lib.check(7, "gpx_potrf")
+    _lib.check(0)
+
+
+def test_product_package_never_imports_oracle():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "gaussian_process_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
