@@ -51,12 +51,27 @@ def test_regression_golden_ka1(golden):
         assert rel(G.f_prior(Xs, np.zeros((100, 1)), "rbf", 1, 3), g[tag + "_fprior"]) < 1e-8
 
 
-def test_regression_lin_kernel_not_pd_raises():
-    """The reference's sampling Cholesky fails for the rank-1 linear kernel: same exception type."""
+def test_regression_lin_kernel_vs_oracle():
     from gaussian_process_b200 import GP_regression as G
     X, y, Xs = O.synth_c1(16, 50)
+    np.random.seed(0)
+    mu, sd, fp = G.prediction(X, Xs, y, 'lin', 0.5, 2)
+    np.random.seed(0)
+    mu_o, sd_o, fp_o = O.regression_prediction(X, Xs, y, 'lin', 0.5, 2)
+    assert rel(mu, mu_o) < TOL and rel(sd ** 2, sd_o ** 2) < 1e-7 and rel(fp, fp_o) < 1e-4
+
+
+def test_regression_not_positive_definite_raises_linalgerror():
+    """Duplicate test points with a negative 'noise' make the sampling factor indefinite: the reference's
+    failure mode is numpy.linalg.LinAlgError (GP_regression.py:154) and so is ours."""
+    from gaussian_process_b200 import get_engine
+    from gaussian_process_b200._lib import COV_SE
+    eng = get_engine()
+    X = np.linspace(-1, 1, 40)[:, None]
+    Xd = eng.to_device(X)
+    A = eng.cov(COV_SE, Xd, Xd, [1.0, 1.0], diag_add=-0.5, same_x=True)
     with pytest.raises(np.linalg.LinAlgError):
-        G.prediction(X, Xs, y, 'lin', 0.5, 2)
+        eng.potrf(A)
 
 
 def test_regression_vs_oracle_multi_dim():
