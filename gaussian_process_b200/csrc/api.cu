@@ -51,6 +51,7 @@ extern "C" int gpx_destroy(gpx_handle h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
+    gpx_timing_destroy(h);
     if (h->scratch) cudaFree(h->scratch);
     if (h->d_info) cudaFree(h->d_info);
     if (h->d_partial) cudaFree(h->d_partial);
@@ -110,16 +111,21 @@ extern "C" int gpx_gp_fit(gpx_handle h, int kind, const double* X, int64_t n, in
     GPX_REQUIRE(h != nullptr, 1);
     GPX_REQUIRE(np_ == gpx_padded_dim(n), 11);
     // K + s I, lower tiles only, identity padding            (tune...:306-307, CO2...:142-143)
+    gpx_phase_mark(h, GPX_PH_COV);
     GPX_TRY(gpx_cov_build(h, kind, X, n, X, n, D, theta_host, ntheta, s, GPX_COV_SAME_X | GPX_COV_LOWER, A, np_, np_, lda,
                           nullptr, 0));
+    gpx_phase_mark(h, GPX_PH_POTRF);
     int info = gpx_potrf(h, A, np_, lda, dinv);
     if (info != 0) return info;
+    gpx_phase_mark(h, GPX_PH_SOLVE);
     // alpha = L^-T (L^-1 y)                                   (tune...:308-309)
     GPX_CUDA(cudaMemsetAsync(alpha, 0, np_ * sizeof(double), h->stream));
     GPX_CUDA(cudaMemcpyAsync(alpha, y, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     GPX_TRY(gpx_trsv(h, A, np_, lda, dinv, 0, alpha));
     GPX_TRY(gpx_trsv(h, A, np_, lda, dinv, 1, alpha));
-    return gpx_lml(h, A, n, lda, y, alpha, out3);            // tune...:312
+    int r = gpx_lml(h, A, n, lda, y, alpha, out3);           // tune...:312
+    gpx_phase_mark(h, GPX_PH_END);
+    return r;
 }
 
 extern "C" int gpx_gp_fit_grad(gpx_handle h, int kind, const double* X, int64_t n, int D, const double* theta_host,
@@ -129,9 +135,14 @@ extern "C" int gpx_gp_fit_grad(gpx_handle h, int kind, const double* X, int64_t 
     if (r != 0) return r;
     // K_y^-1 = L^-T L^-1 (tune...:144): in-place triangular inverse, then one triangular SYRK into Kinv.
     // Kinv doubles as the trtri workspace (it is overwritten by lauum afterwards).
+    gpx_phase_mark(h, GPX_PH_TRTRI);
     GPX_TRY(gpx_trtri(h, A, np_, lda, dinv, Kinv));
+    gpx_phase_mark(h, GPX_PH_LAUUM);
     GPX_TRY(gpx_lauum(h, A, np_, lda, Kinv, lda));
-    return gpx_lml_grad(h, kind, X, n, D, theta_host, ntheta, Kinv, lda, alpha, grad);  // tune...:43-57
+    gpx_phase_mark(h, GPX_PH_GRAD);
+    r = gpx_lml_grad(h, kind, X, n, D, theta_host, ntheta, Kinv, lda, alpha, grad);  // tune...:43-57
+    gpx_phase_mark(h, GPX_PH_END);
+    return r;
 }
 
 extern "C" int gpx_host_lml(gpx_handle h, int kind, const double* X, int64_t n, int D, const double* theta, int ntheta,
@@ -204,6 +215,38 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(int iters, double* out) 
     for (int i = 0; i < 16; ++i) s += c[i];
     if (s == 12345.678) out[0] = s;
 }
+// mixed: even warps issue DMMA, odd warps issue DFMA (8x the iterations: one DFMA warp-instruction is
+// 2 issue cycles, one DMMA 16) -- tells whether the two FP64 pipes run concurrently.
+__global__ void __launch_bounds__(256) mixed_peak_kernel(int iters, double* out) {
+    const int warp = threadIdx.x >> 5;
+    double s = 0.0;
+    double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+    if (warp & 1) {
+        double c[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) c[i] = threadIdx.x * 1e-3 + i;
+        for (int it = 0; it < iters * 8; ++it) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) c[i] = fma(c[i], a, 1e-9);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s += c[i];
+    } else {
+        double c[16][2];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) c[i][0] = c[i][1] = 0.0;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                             : "+d"(c[i][0]), "+d"(c[i][1])
+                             : "d"(a), "d"(b));
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s += c[i][0] + c[i][1];
+    }
+    if (s == 12345.678) out[0] = s;
+}
 }  // namespace
 
 extern "C" int gpx_bench_fp64_peak(gpx_handle h, int use_dmma, int iters, double* tflops_out, double* ms_out) {
@@ -213,9 +256,12 @@ extern "C" int gpx_bench_fp64_peak(gpx_handle h, int use_dmma, int iters, double
     GPX_CUDA(cudaEventCreate(&e1));
     const int blocks = 148 * 4, threads = 256;
     double best = 1e30;
-    for (int rep = 0; rep < 4; ++rep) {
+    // spin the clocks up first (an idle GPU needs tens of ms to reach its boost clock)
+    for (int w = 0; w < 12; ++w) dmma_peak_kernel<<<blocks, threads, 0, h->stream>>>(iters, h->d_theta);
+    for (int rep = 0; rep < 8; ++rep) {
         GPX_CUDA(cudaEventRecord(e0, h->stream));
-        if (use_dmma) dmma_peak_kernel<<<blocks, threads, 0, h->stream>>>(iters, h->d_theta);
+        if (use_dmma == 2) mixed_peak_kernel<<<blocks, threads, 0, h->stream>>>(iters, h->d_theta);
+        else if (use_dmma) dmma_peak_kernel<<<blocks, threads, 0, h->stream>>>(iters, h->d_theta);
         else dfma_peak_kernel<<<blocks, threads, 0, h->stream>>>(iters, h->d_theta);
         GPX_CHECK_LAUNCH(h);
         GPX_CUDA(cudaEventRecord(e1, h->stream));
@@ -227,7 +273,8 @@ extern "C" int gpx_bench_fp64_peak(gpx_handle h, int use_dmma, int iters, double
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     const double warps = (double)blocks * threads / 32.0;
-    const double flops = use_dmma ? warps * iters * 16.0 * 512.0 : warps * iters * 16.0 * 64.0;
+    double flops = use_dmma ? warps * iters * 16.0 * 512.0 : warps * iters * 16.0 * 64.0;
+    if (use_dmma == 2) flops = 0.5 * warps * iters * 16.0 * 512.0 + 0.5 * warps * iters * 8.0 * 16.0 * 64.0;
     *ms_out = best;
     *tflops_out = flops / (best * 1e-3) / 1e12;
     return 0;

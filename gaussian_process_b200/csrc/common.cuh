@@ -21,7 +21,17 @@ struct gpx_ctx {
     // NCCL (optional, dlopen'ed)
     void* nccl_comm; int rank, world;
     cudaStream_t aux_stream; cudaEvent_t ev_a, ev_b;
+    // optional instrumentation (timing.cu)
+    int timing_on; void* timing;
 };
+
+// phases of the fused drivers (gpx_timing_collect out[3 + phase])
+enum { GPX_PH_COV = 0, GPX_PH_POTRF = 1, GPX_PH_SOLVE = 2, GPX_PH_TRTRI = 3, GPX_PH_LAUUM = 4, GPX_PH_GRAD = 5,
+       GPX_PH_END = 6, GPX_NPHASES = 8 };
+void gpx_timing_gemm_begin(gpx_ctx* h, double flops_exec);
+void gpx_timing_gemm_end(gpx_ctx* h);
+void gpx_phase_mark(gpx_ctx* h, int phase);
+void gpx_timing_destroy(gpx_ctx* h);
 
 void gpx_set_error(const char* fmt, ...);
 

@@ -153,8 +153,21 @@ int launch_t(gpx_ctx* h, const GemmArgs& a) {
         configured = true;
     }
     dim3 grid(a.N / BN, a.M / BM, a.batch > 0 ? a.batch : 1);
+    if (h->timing_on) {  // flops the launch really executes (tile-granular k ranges)
+        double ksum = 0.0;
+        for (int bm = 0; bm < (int)grid.y; ++bm)
+            for (int bn = 0; bn < (int)grid.x; ++bn) {
+                if (a.lower_only && bn > bm) continue;
+                int kb = a.kb_mode == 1 ? bm * BM : (a.kb_mode == 2 ? bn * BN : 0);
+                int ke = a.ke_mode == 1 ? bm * BM + BM : (a.ke_mode == 2 ? bn * BN + BN : a.K);
+                if (ke > a.K) ke = a.K;
+                if (ke > kb) ksum += (double)(ke - kb);
+            }
+        gpx_timing_gemm_begin(h, 2.0 * BM * BN * ksum * grid.z);
+    }
     dgemm_dmma_kernel<A_KM, B_KM><<<grid, NTHREADS, SMEM_BYTES, h->stream>>>(a);
     GPX_CHECK_LAUNCH(h);
+    gpx_timing_gemm_end(h);
     return 0;
 }
 

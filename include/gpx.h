@@ -169,6 +169,13 @@ int gpx_dot(gpx_handle h, int64_t n, const double* x, const double* y, double* o
  * register-resident DMMA.8x8x4 / DFMA issue-rate microbenchmarks -> measured FP64 peaks (TFLOP/s). */
 int gpx_bench_fp64_peak(gpx_handle h, int use_dmma, int iters, double* tflops_out, double* ms_out);
 
+/* CUDA-event instrumentation (off by default).  After gpx_timing_enable(h,1), every DMMA GEMM launch and
+ * every phase of the fused drivers is bracketed by events; gpx_timing_collect synchronises and returns
+ * out[0] = GEMM kernel ms, out[1] = #GEMM launches, out[2] = flops executed by them, out[3+p] = ms in
+ * phase p (0 cov build, 1 potrf, 2 solves+LML, 3 trtri, 4 lauum, 5 gradient).  nout >= 11. */
+int gpx_timing_enable(gpx_handle h, int on);
+int gpx_timing_collect(gpx_handle h, double* out, int nout);
+
 /* ---- multi-GPU (one process per GPU; NCCL communicator owned by the handle) -----------------*/
 int gpx_nccl_unique_id(void* id128);                                  /* rank 0: fills 128 bytes */
 int gpx_nccl_init(gpx_handle h, const void* id128, int rank, int world);
