@@ -38,11 +38,13 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gpx", choices=["gpx", "reference"])
-    ap.add_argument("--n", type=int, default=65536, help="training points (BASELINE config: 65536)")
-    ap.add_argument("--d", type=int, default=16)
+    ap.add_argument("--npoints", dest="n", type=int, default=65536, help="training points (BASELINE config: 65536)")
+    ap.add_argument("--dim", dest="d", type=int, default=16)
     ap.add_argument("--cpu-sample-n", type=int, default=4096, help="size of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--block", dest="nb", type=int, default=512, help="block-cyclic block width of the multi-GPU path")
+    ap.add_argument("--mg", action="store_true", help="use the block-cyclic multi-GPU driver even at world size 1")
     return ap.parse_args()
 
 
@@ -171,22 +173,32 @@ def run_gpx(args):
     theta = np.array([SIGMA, ELL])
     thp = theta.ctypes.data_as(ctypes.c_void_p)
 
-    # measured FP64 peaks (no FP64 figure exists in MEASURED_PEAKS.json): register-resident issue loops
-    dmma_peak, _ = eng.fp64_peak(True, 8192)
-    dfma_peak, _ = eng.fp64_peak(False, 8192)
-
     Xd, yd = eng.to_device(X), eng.to_device(y)
-    A = eng.empty(npad, npad)
-    Kinv = eng.empty(npad, npad)
-    dinv = eng.empty(npad // 128, 128, 128)
-    alpha = eng.empty(npad)
+    use_mg = world > 1 or args.mg
     out = eng.empty(16)
     gradp = ctypes.c_void_p(out.data_ptr() + 24)
+    if use_mg:
+        if world > 1:
+            eng.mg_init()
+        npad = int(lib.gpx_mg_padded_dim(n, args.nb, world))
+        ws = eng.empty(int(lib.gpx_mg_workspace_elems(n, args.nb, world)))
+        alpha = eng.empty(npad)
+        A = Kinv = None
 
-    def step():
-        eng._sync_stream()
-        check(lib.gpx_gp_fit_grad(eng.h, COV_SE, eng._p(Xd), n, D, thp, 2, S_NOISE, eng._p(yd), eng._p(A), npad, A.stride(0),
-                                  eng._p(dinv), eng._p(Kinv), eng._p(alpha), eng._p(out), gradp), "gpx_gp_fit_grad")
+        def step():
+            eng._sync_stream()
+            check(lib.gpx_mg_fit_grad(eng.h, COV_SE, eng._p(Xd), n, D, thp, 2, S_NOISE, eng._p(yd), args.nb, eng._p(ws),
+                                      eng._p(alpha), eng._p(out), gradp, 1), "gpx_mg_fit_grad")
+    else:
+        A = eng.empty(npad, npad)
+        Kinv = eng.empty(npad, npad)
+        dinv = eng.empty(npad // 128, 128, 128)
+        alpha = eng.empty(npad)
+
+        def step():
+            eng._sync_stream()
+            check(lib.gpx_gp_fit_grad(eng.h, COV_SE, eng._p(Xd), n, D, thp, 2, S_NOISE, eng._p(yd), eng._p(A), npad, A.stride(0),
+                                      eng._p(dinv), eng._p(Kinv), eng._p(alpha), eng._p(out), gradp), "gpx_gp_fit_grad")
 
     def barrier():
         if world > 1:
@@ -213,6 +225,10 @@ def run_gpx(args):
     check(lib.gpx_timing_collect(eng.h, tbuf, 16), "gpx_timing_collect")
     check(lib.gpx_timing_enable(eng.h, 0), "gpx_timing_enable")
     launches = eng.launches() - launches0
+    # measured FP64 peaks (MEASURED_PEAKS.json has no FP64 figure): register-resident issue loops, taken right after
+    # the timed region while the GPU is at its loaded clocks
+    dmma_peak, _ = eng.fp64_peak(True, 8192)
+    dfma_peak, _ = eng.fp64_peak(False, 8192)
     if world > 1:
         t = torch.tensor([ms_total], device=eng.device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -232,14 +248,26 @@ def run_gpx(args):
     if not args.no_e2e:
         del A, Kinv
         torch.cuda.empty_cache()
-        Xh = torch.from_numpy(X).pin_memory().numpy()
-        yh = torch.from_numpy(y).pin_memory().numpy()
+        Xh = torch.from_numpy(X).pin_memory()
+        yh = torch.from_numpy(y).pin_memory()
         lml_h = ctypes.c_double()
         grad_h = (ctypes.c_double * 2)()
 
-        def host_step():
-            check(lib.gpx_host_lml(eng.h, COV_SE, Xh.ctypes.data_as(ctypes.c_void_p), n, D, thp, 2, S_NOISE,
-                                   yh.ctypes.data_as(ctypes.c_void_p), ctypes.byref(lml_h), grad_h), "gpx_host_lml")
+        if use_mg:
+            def host_step():   # host X, y -> device every step; LML + gradient read back every step
+                xd = Xh.to(eng.device, non_blocking=True)
+                yd2 = yh.to(eng.device, non_blocking=True)
+                eng._sync_stream()
+                check(lib.gpx_mg_fit_grad(eng.h, COV_SE, eng._p(xd), n, D, thp, 2, S_NOISE, eng._p(yd2), args.nb, eng._p(ws),
+                                          eng._p(alpha), eng._p(out), gradp, 1), "gpx_mg_fit_grad")
+                o = out.cpu()
+                lml_h.value = float(o[0])
+        else:
+            Xn, yn = Xh.numpy(), yh.numpy()
+
+            def host_step():
+                check(lib.gpx_host_lml(eng.h, COV_SE, Xn.ctypes.data_as(ctypes.c_void_p), n, D, thp, 2, S_NOISE,
+                                       yn.ctypes.data_as(ctypes.c_void_p), ctypes.byref(lml_h), grad_h), "gpx_host_lml")
 
         host_step()                               # warm-up (allocates the handle's scratch)
         barrier()
@@ -270,7 +298,8 @@ def run_gpx(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "C5 tune_hyperparms_regression LML+grad N=%d D=%d (SE kernel, s=5e-4)" % (n, D),
                    "l2": "inputs (2 x %.1f GB matrices) larger than L2; no flush needed" % (npad * npad * 8 / 1e9),
-                   "parallelism": "single GPU" if world == 1 else "replicated x%d" % world},
+                   "parallelism": ("single GPU" if not use_mg else
+                                   "1-D block-cyclic block columns (nb=%d) over %d GPU(s), NCCL panel broadcast + all-gather" % (args.nb, world))},
         "e2e": e2e,
         "gpu_launches": int(launches),
         "clocks": clocks,

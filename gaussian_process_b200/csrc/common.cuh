@@ -77,11 +77,28 @@ struct GemmArgs {
     int64_t sA, sB, sC; int batch;   // strided batch (elements)
     int a_kmajor, b_kmajor;     // 1: operand stored with k contiguous ([M][K] / [N][K]); 0: [K][M] / [K][N]
     int lower_only;             // skip output tiles strictly above the diagonal
-    int kb_mode;                // first k: 0 -> 0, 1 -> tile row0, 2 -> tile col0
+    int kb_mode;                // first k: 0 -> 0, 1 -> tile row0, 2 -> tile col0, 3 -> block-cyclic mapped column position
     int ke_mode;                // last  k: 0 -> K, 1 -> tile row0+128, 2 -> tile col0+128
     int rev_rows;               // schedule tile rows in reverse (longest k-loops first)
+    int64_t kb_batch;           // added to the first k per batch index (batched triangular products)
+    int kb_const;               // constant added to the first k
+    // block-cyclic column map (multi-GPU trailing update): local column tile bn of C corresponds to the
+    // global tile ((bn / cyc_tpb + cyc_q0) * cyc_P + cyc_p) * cyc_tpb + bn % cyc_tpb; its offset relative to
+    // cyc_row_base (global row of C row 0) is used for the lower-only test and as B's row offset.
+    int cyc_P, cyc_p, cyc_tpb, cyc_q0, cyc_row_base;
+    int cyc_b_rows;             // 1: the mapped position is also B's row offset (trailing update); 0: B uses the local column
 };
 int gpx_gemm_launch(gpx_ctx* h, const GemmArgs& a);
 
+int gpx_lml_grad_block(gpx_ctx* h, int kind, const double* X, int64_t n, int D, const double* theta_host, int ntheta,
+                       const double* Kinv, int64_t ldk, const double* alpha, double* grad, int64_t rows, int64_t cols, int rg0,
+                       int cg0);
+int gpx_cov_build_block(gpx_ctx* h, int kind, const double* X, int64_t n, int D, const double* theta_host, int ntheta,
+                        double diag_add, int flags, double* K, int64_t rows, int64_t cols, int64_t ldk, int rg0, int cg0);
+int gpx_potrf_block(gpx_ctx* h, double* A, int64_t n, int64_t lda, double* dinv, int goff);
+int gpx_trsm_right_lt_block(gpx_ctx* h, double* B, int64_t m, int64_t ldb, const double* L, int64_t n, int64_t ldl,
+                            const double* dinv);
+int gpx_trsm_left_prefix_block(gpx_ctx* h, const double* L, int64_t n, int64_t ldl, const double* dinv, double* B, int64_t ldb,
+                               int P, int p, int nb);
 int gpx_scratch(gpx_ctx* h, size_t bytes, void** out);
 int gpx_read_info(gpx_ctx* h, int* info_host);

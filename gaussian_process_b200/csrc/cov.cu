@@ -132,12 +132,17 @@ template <int KIND, bool WITH_DK>
 __global__ void __launch_bounds__(CTHREADS) cov_build_kernel(CovParams p, const double* __restrict__ X1, int64_t n1,
                                                             const double* __restrict__ X2, int64_t n2, double diag_add,
                                                             int flags, double* __restrict__ K, int64_t ldk,
-                                                            double* __restrict__ dK, int64_t dk_stride) {
+                                                            double* __restrict__ dK, int64_t dk_stride, int rg0, int cg0) {
+    // rg0 / cg0: global row / column index of this launch's element (0,0) -- K points at that element; used by
+    // the multi-GPU driver to build only the block columns a rank owns.
     __shared__ double xs1[TM * DCH];
     __shared__ double xs2[DCH * TN];
-    const int row0 = blockIdx.y * TM, col0 = blockIdx.x * TN;
+    const int lrow0 = blockIdx.y * TM, lcol0 = blockIdx.x * TN;
+    const int row0 = lrow0 + rg0, col0 = lcol0 + cg0;
     const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
     const bool same = flags & GPX_COV_SAME_X;
+    K -= (int64_t)rg0 * ldk + cg0;  // index with global (row, col) below
+    if (WITH_DK) dK -= (int64_t)rg0 * ldk + cg0;
     if ((flags & GPX_COV_LOWER) && col0 > row0) {  // strictly-upper tile: zeros
 #pragma unroll
         for (int i = 0; i < RI; ++i)
@@ -188,11 +193,13 @@ __global__ void __launch_bounds__(CTHREADS) cov_build_kernel(CovParams p, const 
 template <int KIND>
 __global__ void __launch_bounds__(CTHREADS) lml_grad_kernel(CovParams p, const double* __restrict__ X, int64_t n,
                                                            const double* __restrict__ Kinv, int64_t ldk,
-                                                           const double* __restrict__ alpha, double* __restrict__ partial) {
+                                                           const double* __restrict__ alpha, double* __restrict__ partial,
+                                                           int rg0, int cg0) {
     __shared__ double xs1[TM * DCH];
     __shared__ double xs2[DCH * TN];
     __shared__ double red[CTHREADS / 32][11];
-    const int bm = blockIdx.y, bn = blockIdx.x;
+    const int bm = blockIdx.y + rg0 / TM, bn = blockIdx.x + cg0 / TN;  // global tile indices
+    Kinv -= (int64_t)rg0 * ldk + cg0;
     const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
     const int block_id = blockIdx.y * gridDim.x + blockIdx.x;
     constexpr int NTH = NTheta<KIND>::value;
@@ -278,20 +285,21 @@ int make_params(int kind, int D, const double* theta, int ntheta, CovParams* p) 
 
 template <bool WITH_DK>
 int launch_build(gpx_ctx* h, const CovParams& p, const double* X1, int64_t n1, const double* X2, int64_t n2, double diag_add,
-                 int flags, double* K, int64_t n1p, int64_t n2p, int64_t ldk, double* dK, int64_t dk_stride) {
+                 int flags, double* K, int64_t n1p, int64_t n2p, int64_t ldk, double* dK, int64_t dk_stride, int rg0 = 0,
+                 int cg0 = 0) {
     dim3 grid((unsigned)(n2p / TN), (unsigned)(n1p / TM));
     switch (p.kind) {
         case GPX_COV_SE:
-            cov_build_kernel<GPX_COV_SE, WITH_DK><<<grid, CTHREADS, 0, h->stream>>>(p, X1, n1, X2, n2, diag_add, flags, K, ldk, dK, dk_stride);
+            cov_build_kernel<GPX_COV_SE, WITH_DK><<<grid, CTHREADS, 0, h->stream>>>(p, X1, n1, X2, n2, diag_add, flags, K, ldk, dK, dk_stride, rg0, cg0);
             break;
         case GPX_COV_LIN:
-            cov_build_kernel<GPX_COV_LIN, WITH_DK><<<grid, CTHREADS, 0, h->stream>>>(p, X1, n1, X2, n2, diag_add, flags, K, ldk, dK, dk_stride);
+            cov_build_kernel<GPX_COV_LIN, WITH_DK><<<grid, CTHREADS, 0, h->stream>>>(p, X1, n1, X2, n2, diag_add, flags, K, ldk, dK, dk_stride, rg0, cg0);
             break;
         case GPX_COV_PER:
-            cov_build_kernel<GPX_COV_PER, WITH_DK><<<grid, CTHREADS, 0, h->stream>>>(p, X1, n1, X2, n2, diag_add, flags, K, ldk, dK, dk_stride);
+            cov_build_kernel<GPX_COV_PER, WITH_DK><<<grid, CTHREADS, 0, h->stream>>>(p, X1, n1, X2, n2, diag_add, flags, K, ldk, dK, dk_stride, rg0, cg0);
             break;
         default:
-            cov_build_kernel<GPX_COV_CO2, WITH_DK><<<grid, CTHREADS, 0, h->stream>>>(p, X1, n1, X2, n2, diag_add, flags, K, ldk, dK, dk_stride);
+            cov_build_kernel<GPX_COV_CO2, WITH_DK><<<grid, CTHREADS, 0, h->stream>>>(p, X1, n1, X2, n2, diag_add, flags, K, ldk, dK, dk_stride, rg0, cg0);
             break;
     }
     GPX_CHECK_LAUNCH(h);
@@ -315,14 +323,16 @@ extern "C" int gpx_cov_build(gpx_handle h, int kind, const double* X1, int64_t n
     return launch_build<false>(h, p, X1, n1, X2, n2, diag_add, flags, K, n1p, n2p, ldk, nullptr, 0);
 }
 
-extern "C" int gpx_lml_grad(gpx_handle h, int kind, const double* X, int64_t n, int D, const double* theta_host, int ntheta,
-                            const double* Kinv, int64_t ldk, const double* alpha, double* grad) {
-    GPX_REQUIRE(h != nullptr, 1);
+// Gradient partial sums over the block of K^-1 whose element (0,0) has global index (rg0, cg0) and which spans
+// `rows` x `cols` elements (multiples of 128); grad (device, ntheta doubles) receives this block's contribution.
+int gpx_lml_grad_block(gpx_ctx* h, int kind, const double* X, int64_t n, int D, const double* theta_host, int ntheta,
+                       const double* Kinv, int64_t ldk, const double* alpha, double* grad, int64_t rows, int64_t cols, int rg0,
+                       int cg0) {
     GPX_REQUIRE(kind >= 0 && kind <= 3, 2);
     CovParams p;
     GPX_TRY(make_params(kind, D, theta_host, ntheta, &p));
-    const int nt = (int)((n + TM - 1) / TM);
-    const size_t need = (size_t)nt * nt * ntheta;
+    const int ntr = (int)(rows / TM), ntc = (int)(cols / TN);
+    const size_t need = (size_t)ntr * ntc * ntheta;
     if (h->partial_elems < need) {
         if (h->d_partial) cudaFree(h->d_partial);
         h->d_partial = nullptr;
@@ -333,15 +343,30 @@ extern "C" int gpx_lml_grad(gpx_handle h, int kind, const double* X, int64_t n, 
         }
         h->partial_elems = need;
     }
-    dim3 grid(nt, nt);
+    dim3 grid(ntc, ntr);
     switch (kind) {
-        case GPX_COV_SE: lml_grad_kernel<GPX_COV_SE><<<grid, CTHREADS, 0, h->stream>>>(p, X, n, Kinv, ldk, alpha, h->d_partial); break;
-        case GPX_COV_LIN: lml_grad_kernel<GPX_COV_LIN><<<grid, CTHREADS, 0, h->stream>>>(p, X, n, Kinv, ldk, alpha, h->d_partial); break;
-        case GPX_COV_PER: lml_grad_kernel<GPX_COV_PER><<<grid, CTHREADS, 0, h->stream>>>(p, X, n, Kinv, ldk, alpha, h->d_partial); break;
-        default: lml_grad_kernel<GPX_COV_CO2><<<grid, CTHREADS, 0, h->stream>>>(p, X, n, Kinv, ldk, alpha, h->d_partial); break;
+        case GPX_COV_SE: lml_grad_kernel<GPX_COV_SE><<<grid, CTHREADS, 0, h->stream>>>(p, X, n, Kinv, ldk, alpha, h->d_partial, rg0, cg0); break;
+        case GPX_COV_LIN: lml_grad_kernel<GPX_COV_LIN><<<grid, CTHREADS, 0, h->stream>>>(p, X, n, Kinv, ldk, alpha, h->d_partial, rg0, cg0); break;
+        case GPX_COV_PER: lml_grad_kernel<GPX_COV_PER><<<grid, CTHREADS, 0, h->stream>>>(p, X, n, Kinv, ldk, alpha, h->d_partial, rg0, cg0); break;
+        default: lml_grad_kernel<GPX_COV_CO2><<<grid, CTHREADS, 0, h->stream>>>(p, X, n, Kinv, ldk, alpha, h->d_partial, rg0, cg0); break;
     }
     GPX_CHECK_LAUNCH(h);
-    grad_finish_kernel<<<ntheta, 256, 0, h->stream>>>(nt * nt, ntheta, h->d_partial, grad);
+    grad_finish_kernel<<<ntheta, 256, 0, h->stream>>>(ntr * ntc, ntheta, h->d_partial, grad);
     GPX_CHECK_LAUNCH(h);
     return 0;
+}
+
+// Covariance block whose element (0,0) has global index (rg0, cg0): rows x cols elements written at K (ld ldk).
+int gpx_cov_build_block(gpx_ctx* h, int kind, const double* X, int64_t n, int D, const double* theta_host, int ntheta,
+                        double diag_add, int flags, double* K, int64_t rows, int64_t cols, int64_t ldk, int rg0, int cg0) {
+    CovParams p;
+    GPX_TRY(make_params(kind, D, theta_host, ntheta, &p));
+    return launch_build<false>(h, p, X, n, X, n, diag_add, flags, K, rows, cols, ldk, nullptr, 0, rg0, cg0);
+}
+
+extern "C" int gpx_lml_grad(gpx_handle h, int kind, const double* X, int64_t n, int D, const double* theta_host, int ntheta,
+                            const double* Kinv, int64_t ldk, const double* alpha, double* grad) {
+    GPX_REQUIRE(h != nullptr, 1);
+    const int64_t np_ = ((n + TM - 1) / TM) * TM;
+    return gpx_lml_grad_block(h, kind, X, n, D, theta_host, ntheta, Kinv, ldk, alpha, grad, np_, np_, 0, 0);
 }

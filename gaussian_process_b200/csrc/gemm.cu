@@ -56,13 +56,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgemm_dmma_kernel(GemmArgs p) {
     const int tid = threadIdx.x;
     const int bn = blockIdx.x;
     const int bm = p.rev_rows ? (gridDim.y - 1 - blockIdx.y) : blockIdx.y;
-    if (p.lower_only && bn > bm) return;
     const int row0 = bm * BM, col0 = bn * BN;
+    int gpos = col0;   // position of this column tile in global (block-cyclic) numbering, relative to cyc_row_base
+    if (p.cyc_P > 0) {
+        const int lb = bn / p.cyc_tpb;
+        gpos = (((lb + p.cyc_q0) * p.cyc_P + p.cyc_p) * p.cyc_tpb + bn % p.cyc_tpb) * BN - p.cyc_row_base;
+    }
+    const int brow0 = (p.cyc_P > 0 && !p.cyc_b_rows) ? col0 : gpos;  // offset of this column tile inside the B operand
+    if (p.lower_only && gpos > row0) return;
     const double* __restrict__ A = p.A + (int64_t)blockIdx.z * p.sA;
     const double* __restrict__ B = p.B + (int64_t)blockIdx.z * p.sB;
     double* C = p.C + (int64_t)blockIdx.z * p.sC;
 
-    int kbeg = p.kb_mode == 1 ? row0 : (p.kb_mode == 2 ? col0 : 0);
+    int kbeg = (p.kb_mode == 1 ? row0 : (p.kb_mode == 2 ? col0 : (p.kb_mode == 3 ? gpos : 0))) + (int)(blockIdx.z * p.kb_batch) + p.kb_const;
+    if (kbeg < 0) kbeg = 0;
     int kend = p.ke_mode == 1 ? row0 + BM : (p.ke_mode == 2 ? col0 + BN : p.K);
     if (kend > p.K) kend = p.K;
     const int nk = kend > kbeg ? (kend - kbeg) / BK : 0;
@@ -85,7 +92,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgemm_dmma_kernel(GemmArgs p) {
     for (int st = 0; st < STAGES - 1; ++st) {
         if (st < nk) {
             load_slab<A_KM>(sA(st), A, p.lda, row0, kbeg + st * BK, tid);
-            load_slab<B_KM>(sB(st), B, p.ldb, col0, kbeg + st * BK, tid);
+            load_slab<B_KM>(sB(st), B, p.ldb, brow0, kbeg + st * BK, tid);
         }
         cp_async_commit();
     }
@@ -98,7 +105,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgemm_dmma_kernel(GemmArgs p) {
             if (nxt < nk) {
                 int st = nxt % STAGES;
                 load_slab<A_KM>(sA(st), A, p.lda, row0, kbeg + nxt * BK, tid);
-                load_slab<B_KM>(sB(st), B, p.ldb, col0, kbeg + nxt * BK, tid);
+                load_slab<B_KM>(sB(st), B, p.ldb, brow0, kbeg + nxt * BK, tid);
             }
             cp_async_commit();
         }
@@ -157,13 +164,19 @@ int launch_t(gpx_ctx* h, const GemmArgs& a) {
         double ksum = 0.0;
         for (int bm = 0; bm < (int)grid.y; ++bm)
             for (int bn = 0; bn < (int)grid.x; ++bn) {
-                if (a.lower_only && bn > bm) continue;
-                int kb = a.kb_mode == 1 ? bm * BM : (a.kb_mode == 2 ? bn * BN : 0);
+                int br = bn * BN;
+                if (a.cyc_P > 0) br = (((bn / a.cyc_tpb + a.cyc_q0) * a.cyc_P + a.cyc_p) * a.cyc_tpb + bn % a.cyc_tpb) * BN - a.cyc_row_base;
+                if (a.lower_only && br > bm * BM) continue;
+                int kb = a.kb_mode == 1 ? bm * BM : (a.kb_mode == 2 ? bn * BN : (a.kb_mode == 3 ? br : 0));
                 int ke = a.ke_mode == 1 ? bm * BM + BM : (a.ke_mode == 2 ? bn * BN + BN : a.K);
                 if (ke > a.K) ke = a.K;
-                if (ke > kb) ksum += (double)(ke - kb);
+                for (int z = 0; z < (int)grid.z; ++z) {
+                    int kbz = kb + (int)(z * a.kb_batch) + a.kb_const;
+                    if (kbz < 0) kbz = 0;
+                    if (ke > kbz) ksum += (double)(ke - kbz);
+                }
             }
-        gpx_timing_gemm_begin(h, 2.0 * BM * BN * ksum * grid.z);
+        gpx_timing_gemm_begin(h, 2.0 * BM * BN * ksum);
     }
     dgemm_dmma_kernel<A_KM, B_KM><<<grid, NTHREADS, SMEM_BYTES, h->stream>>>(a);
     GPX_CHECK_LAUNCH(h);

@@ -321,3 +321,60 @@ extern "C" int gpx_lauum(gpx_handle h, const double* Linv, int64_t n, int64_t ld
     a.kb_mode = 1;
     return gpx_gemm_launch(h, a);
 }
+
+// ---- internal entry points used by the multi-GPU driver (nccl_mg.cu) --------------------------------
+int gpx_potrf_block(gpx_ctx* h, double* A, int64_t n, int64_t lda, double* dinv, int goff) {
+    return potrf_rec(h, A, n, lda, dinv, goff);
+}
+int gpx_trsm_right_lt_block(gpx_ctx* h, double* B, int64_t m, int64_t ldb, const double* L, int64_t n, int64_t ldl,
+                            const double* dinv) {
+    return trsm_right_lt(h, B, m, ldb, L, n, ldl, dinv);
+}
+
+namespace {
+// Left lower TRSM  L X = B  where only a *prefix* of B's columns is non-zero in any given row range: for rows
+// below global row r (relative to this sub-problem's row 0 at global row `grow0`), the non-zero columns are the
+// local blocks whose global block index is <= block(r): count = prefix(r).  Used for L^-1 on block-cyclic columns.
+struct PrefixMap { int P, p, nb; };
+inline int64_t prefix_cols(const PrefixMap& pm, int64_t grow_end) {
+    // number of local columns (elements) whose global block start is < grow_end
+    const int64_t nblk_below = (grow_end + pm.nb - 1) / pm.nb;              // global blocks 0..nblk_below-1 start below grow_end
+    const int64_t cnt = nblk_below > pm.p ? (nblk_below - pm.p + pm.P - 1) / pm.P : 0;  // those owned by rank p
+    return cnt * pm.nb;
+}
+int trsm_left_prefix(gpx_ctx* h, const double* L, int64_t n, int64_t ldl, const double* dinv, double* B, int64_t ldb,
+                     int64_t grow0, const PrefixMap& pm) {
+    const int64_t ncols = prefix_cols(pm, grow0 + n);   // columns that can be non-zero within these rows
+    if (ncols <= 0) return 0;
+    if (n == LT) {
+        GemmArgs a = base_args();
+        a.A = dinv; a.lda = LT; a.a_kmajor = 1;
+        a.B = B; a.ldb = ldb; a.b_kmajor = 0;
+        a.C = B; a.ldc = ldb;
+        a.M = LT; a.N = (int)ncols; a.K = LT;
+        return gpx_gemm_launch(h, a);
+    }
+    const int64_t h1 = half_tiles(n), h2 = n - h1;
+    GPX_TRY(trsm_left_prefix(h, L, h1, ldl, dinv, B, ldb, grow0, pm));
+    const int64_t nc1 = prefix_cols(pm, grow0 + h1);   // X1 is non-zero only in these columns
+    if (nc1 > 0) {
+        GemmArgs a = base_args();  // B2[:, :nc1] -= L21 X1[:, :nc1]
+        a.A = L + h1 * ldl; a.lda = ldl; a.a_kmajor = 1;
+        a.B = B; a.ldb = ldb; a.b_kmajor = 0;
+        a.C = B + h1 * ldb; a.ldc = ldb;
+        a.M = (int)h2; a.N = (int)nc1; a.K = (int)h1;
+        a.alpha = -1.0; a.beta = 1.0;
+        // X1[k][c] is zero for global rows above the start of c's block: begin the k loop there
+        a.kb_mode = 3; a.cyc_P = pm.P; a.cyc_p = pm.p; a.cyc_tpb = pm.nb / LT; a.cyc_q0 = 0; a.cyc_row_base = (int)grow0;
+        a.cyc_b_rows = 0;
+        GPX_TRY(gpx_gemm_launch(h, a));
+    }
+    return trsm_left_prefix(h, L + h1 * ldl + h1, h2, ldl, dinv + (h1 / LT) * LT * LT, B + h1 * ldb, ldb, grow0 + h1, pm);
+}
+}  // namespace
+
+int gpx_trsm_left_prefix_block(gpx_ctx* h, const double* L, int64_t n, int64_t ldl, const double* dinv, double* B, int64_t ldb,
+                               int P, int p, int nb) {
+    PrefixMap pm{P, p, nb};
+    return trsm_left_prefix(h, L, n, ldl, dinv, B, ldb, 0, pm);
+}

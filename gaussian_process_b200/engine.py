@@ -7,6 +7,7 @@ no CPU fallback -- constructing an :class:`Engine` without the library or withou
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass
 from typing import Optional, Sequence
 
@@ -297,6 +298,64 @@ class Engine:
         out = self.empty(mp, padded(nf))
         self.gemm(Lfac, Zp, out, a_kmajor=True, b_kmajor=False, M=mp, N=padded(nf), K=mp)
         return self.to_host(out[:n, :nf])
+
+    # ------------------------------------------------------------------ multi-GPU (one process per GPU)
+    def mg_init(self):
+        """Create libgpx's own NCCL communicator over the ranks of the initialised torch.distributed group
+        (the 128-byte NCCL unique id travels through torch.distributed; NCCL itself is dlopen'ed by libgpx)."""
+        import torch.distributed as dist
+        if getattr(self, "_mg_ready", False):
+            return
+        world, rank = dist.get_world_size(), dist.get_rank()
+        if world > 1:
+            import nvidia.nccl as _n  # torch-bundled libnccl.so.2
+            path = os.path.join(os.path.dirname(_n.__file__) if getattr(_n, "__file__", None) else list(_n.__path__)[0],
+                                "lib", "libnccl.so.2")
+            check(self.lib.gpx_nccl_load(path.encode()), "gpx_nccl_load")
+            ident = (ctypes.c_char * 128)()
+            if rank == 0:
+                check(self.lib.gpx_nccl_unique_id(ident), "gpx_nccl_unique_id")
+            t = self.torch.tensor(list(ident.raw), dtype=self.torch.uint8, device=self.device)
+            dist.broadcast(t, src=0)
+            raw = bytes(t.cpu().tolist())
+            buf = (ctypes.c_char * 128).from_buffer_copy(raw)
+            check(self.lib.gpx_nccl_init(self.h, buf, rank, world), "gpx_nccl_init")
+        self._mg_ready = True
+        self._mg_world, self._mg_rank = world, rank
+
+    def mg_fit_grad(self, kind: int, X, y, theta, s: float, nb: int = 512, with_grad: bool = True, ws=None):
+        """Distributed fit + LML (+ gradient) over the ranks of ``mg_init`` -> (lml, grad ndarray or None, alpha dev)."""
+        self._sync_stream()
+        world = getattr(self, "_mg_world", 1)
+        Xd, yd = self.to_device(X), self.to_device(np.asarray(y).reshape(-1) if not hasattr(y, "data_ptr") else y.reshape(-1))
+        n, D = Xd.shape
+        th, thp = _theta_array(theta)
+        npad = int(self.lib.gpx_mg_padded_dim(n, nb, world))
+        if ws is None:
+            ws = self.empty(int(self.lib.gpx_mg_workspace_elems(n, nb, world)))
+        alpha = self.empty(npad)
+        out = self.empty(3 + 11)
+        st = self.lib.gpx_mg_fit_grad(self.h, kind, self._p(Xd), n, D, thp, len(th), float(s), self._p(yd), nb, self._p(ws),
+                                      self._p(alpha), self._p(out), ctypes.c_void_p(out.data_ptr() + 24), int(with_grad))
+        check(st, "gpx_mg_fit_grad")
+        o = self.to_host(out)
+        return float(o[0]), (o[3:3 + len(th)].copy() if with_grad else None), alpha
+
+    def mg_emulate_fit_grad(self, P: int, kind: int, X, y, theta, s: float, nb: int = 256):
+        """P virtual ranks on this one GPU (test helper for the block-cyclic index maps)."""
+        self._sync_stream()
+        Xd, yd = self.to_device(X), self.to_device(np.asarray(y).reshape(-1))
+        n, D = Xd.shape
+        th, thp = _theta_array(theta)
+        npad = int(self.lib.gpx_mg_padded_dim(n, nb, P))
+        ws = self.empty(P * int(self.lib.gpx_mg_workspace_elems(n, nb, P)))
+        alpha = self.empty(npad)
+        out = self.empty(3 + 11)
+        st = self.lib.gpx_mg_emulate_fit_grad(self.h, P, kind, self._p(Xd), n, D, thp, len(th), float(s), self._p(yd), nb,
+                                              self._p(ws), self._p(alpha), self._p(out), ctypes.c_void_p(out.data_ptr() + 24))
+        check(st, "gpx_mg_emulate_fit_grad")
+        o = self.to_host(out)
+        return float(o[0]), o[3:3 + len(th)].copy(), self.to_host(alpha[:n])
 
     # ------------------------------------------------------------------ measurement
     def fp64_peak(self, dmma: bool = True, iters: int = 4096):

@@ -176,11 +176,25 @@ int gpx_bench_fp64_peak(gpx_handle h, int use_dmma, int iters, double* tflops_ou
 int gpx_timing_enable(gpx_handle h, int on);
 int gpx_timing_collect(gpx_handle h, double* out, int nout);
 
-/* ---- multi-GPU (one process per GPU; NCCL communicator owned by the handle) -----------------*/
-int gpx_nccl_unique_id(void* id128);                                  /* rank 0: fills 128 bytes */
-int gpx_nccl_init(gpx_handle h, const void* id128, int rank, int world);
-/* 1-D block-cyclic (column blocks of `nb`) right-looking Cholesky with NCCL panel broadcast.
- * Aloc: n x (local columns) row-major, local column block q holds global block q*world+rank. */
+/* ---- multi-GPU (one process per GPU; NCCL communicator owned by the handle) -----------------
+ * Layout: 1-D block-cyclic block columns of width nb (a P x 1 grid of the 2-D block-cyclic scheme), panels
+ * broadcast with NCCL and kept in a replicated factor; see nccl_mg.cu.  NCCL is dlopen'ed at run time. */
+int     gpx_nccl_load(const char* libnccl_path);                        /* optional explicit path */
+int     gpx_nccl_unique_id(void* id128);                                /* rank 0: fills 128 bytes */
+int     gpx_nccl_init(gpx_handle h, const void* id128, int rank, int world);
+int64_t gpx_mg_padded_dim(int64_t n, int nb, int world);                /* n rounded up to nb*world */
+int64_t gpx_mg_workspace_elems(int64_t n, int nb, int world);           /* doubles of device workspace per rank */
+/* This rank's part of the distributed fit + LML (+ gradient when with_grad): tune...:123-145 on P GPUs.
+ * X (n x D), y (n), alpha (npad), out3 (3), grad (ntheta) are device pointers; every rank gets the same
+ * alpha / out3 / grad.  Returns >0 (first bad pivot) on every rank if the matrix is not positive definite. */
+int gpx_mg_fit_grad(gpx_handle h, int kind, const double* X, int64_t n, int D, const double* theta_host, int ntheta,
+                    double s, const double* y, int nb, double* ws, double* alpha, double* out3, double* grad, int with_grad);
+/* Test helper: the same per-rank routines driven for P virtual ranks on ONE GPU (collectives become copies);
+ * ws_all = P * gpx_mg_workspace_elems(n, nb, P) doubles. */
+int gpx_mg_emulate_fit_grad(gpx_handle h, int P, int kind, const double* X, int64_t n, int D, const double* theta_host,
+                            int ntheta, double s, const double* y, int nb, double* ws_all, double* alpha, double* out3,
+                            double* grad);
+/* legacy name kept for ABI stability: returns GPX_E_ARG (use gpx_mg_fit_grad) */
 int gpx_potrf_mg(gpx_handle h, double* Aloc, int64_t n, int64_t ldl, int64_t nb, double* panel, double* dinv);
 
 /* ---- host-buffer drop-in calls (HOST pointers; copies inside; synchronous) ------------------*/
