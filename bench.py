@@ -239,8 +239,10 @@ def run_gpx(args):
 
     gemm_ms, gemm_launches, gemm_flops_exec = tbuf[0] / args.steps, tbuf[1] / args.steps, tbuf[2] / args.steps
     phases = {k: tbuf[3 + i] / args.steps for i, k in enumerate(["cov_build", "potrf", "solves_lml", "trtri", "lauum", "gradient"])}
-    alg_flops = float(npad) ** 3                 # potrf N^3/3 + trtri N^3/3 + lauum N^3/3
-    achieved = alg_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    alg_flops = float(padded(n)) ** 3            # potrf N^3/3 + trtri N^3/3 + lauum N^3/3
+    # per-GPU roofline: this rank's share of the algorithmic flops over this rank's DMMA-GEMM kernel time
+    achieved = (alg_flops / world) / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    npad = float(padded(n))
     potrf_tflops = (float(npad) ** 3 / 3) / (phases["potrf"] * 1e-3) / 1e12 if phases["potrf"] > 0 else 0.0
 
     # ---- e2e: host buffers through the C ABI (H2D + D2H inside the timed region)
@@ -305,7 +307,7 @@ def run_gpx(args):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s",
                      "frac": achieved / dmma_peak if dmma_peak else None, "traffic": None,
-                     "kernel": "dgemm_dmma_kernel (FP64 DMMA.8x8x4)", "alg_flops_per_step": alg_flops,
+                     "kernel": "dgemm_dmma_kernel (FP64 DMMA.8x8x4)", "alg_flops_per_step": alg_flops, "per": "GPU (rank 0)",
                      "kernel_ms_per_step": gemm_ms, "kernel_launches_per_step": gemm_launches,
                      "kernel_flops_executed_per_step": gemm_flops_exec,
                      "peak_source": "measured in this run: register-resident DMMA.8x8x4 issue loop on 148 SMs "
