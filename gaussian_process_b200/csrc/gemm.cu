@@ -1,23 +1,36 @@
-// FP64 tensor-core GEMM for sm_100a: C = alpha * op(A) op(B) + beta * C on 128x128 tiles.
+// FP64 tensor-core GEMM for sm_100a: C = alpha * op(A) op(B) + beta * C on 128 x TN output tiles.
 //
 // Tensor path: mma.sync.aligned.m8n8k4.f64 (SASS DMMA.8x8x4 -- the only FP64 tensor instruction on
-// sm_100a; tcgen05.mma has no f64 kind).  One CTA = 8 warps (2 x 4), warp tile 64 x 32 =
-// 8 x 4 DMMA fragments (32 independent accumulators per warp), K slab 16, 4-stage cp.async
-// (LDGSTS) pipeline into padded shared memory laid out so every 64-bit fragment load is
-// bank-conflict free:
+// sm_100a; tcgen05.mma has no f64 kind, and DMMA shares the FP64 FMA units so 128 flop/clk/SM is the
+// ceiling).  Warp tile 64 x 32 = 8 x 4 DMMA fragments (32 independent accumulators per warp), K slab 16,
+// multi-stage cp.async (LDGSTS) pipeline into padded shared memory laid out so every 64-bit fragment
+// load is bank-conflict free:
 //   k-major operand  : smem[row][16+4]   lane(g,t) reads [r0+g][kk+t]  -> bank8 = 4g+t   (distinct)
-//   k-strided operand: smem[k][128+4]    lane(g,t) reads [kk+t][c0+g]  -> bank8 = 4t+g   (distinct)
-// This kernel is the trailing update (SYRK/GEMM), the TRSM/TRTRI/LAUUM work-horse and the
-// prediction TRSM; triangular structure is exploited at tile granularity through per-tile k ranges.
+//   k-strided operand: smem[k][T+4]      lane(g,t) reads [kk+t][c0+g]  -> bank8 = 4t+g   (distinct)
+// Two tile configurations:
+//   TN = 128 : one CTA of 8 warps per SM (in-place right-TRSM leaves need the whole 128-wide row block)
+//   TN =  64 : CTAs of 4 warps, TWO resident per SM -- while one CTA sits in its prologue / epilogue /
+//              __syncthreads the other keeps the DMMA pipe busy (hardware "ping-pong"); default.
+// This kernel is the trailing update (SYRK/GEMM), the TRSM/TRTRI/LAUUM work-horse and the prediction
+// TRSM; triangular structure is exploited at tile granularity through per-tile k ranges.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, NTHREADS = 256;
-constexpr int KC_LD = BK + 4;       // 20 doubles
-constexpr int KS_LD = 128 + 4;      // 132 doubles
-constexpr int OP_ELEMS = 128 * KC_LD;  // 2560 doubles per operand per stage (>= 16*132)
-constexpr int SMEM_BYTES = STAGES * 2 * OP_ELEMS * (int)sizeof(double);  // 163840
+constexpr int BM = 128, BK = 16;
+constexpr int KC_LD = BK + 4;  // 20 doubles per row of a k-major slab
+
+template <int TN>
+struct Cfg {
+    static constexpr int NT = TN * 2;                     // threads: 8 warps (TN=128) or 4 warps (TN=64)
+    static constexpr int WN = TN / 32;                    // warps along N
+    static constexpr int STAGES = (TN == 128) ? 4 : 3;
+    static constexpr int A_ELEMS = 128 * KC_LD;           // >= 16 * 132
+    static constexpr int B_ELEMS = (TN * KC_LD > 16 * (TN + 4)) ? TN * KC_LD : 16 * (TN + 4);
+    static constexpr int SMEM = STAGES * (A_ELEMS + B_ELEMS) * (int)sizeof(double);
+    static constexpr int MIN_CTAS = (TN == 128) ? 1 : 2;
+};
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -33,50 +46,59 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                  : "d"(a), "d"(b));
 }
 
-// global -> shared for one operand slab.  KMAJOR: 128 rows x 16 k (row r = P[(r0+r)*ld + k0 ..]);
-// else 16 k-rows x 128 (row kr = P[(k0+kr)*ld + r0 ..]).
-template <bool KMAJOR>
+// global -> shared for one operand slab of ROWS "rows".  KMAJOR: ROWS x 16 k (row r = P[(r0+r)*ld + k0 ..]);
+// else 16 k-rows x ROWS (row kr = P[(k0+kr)*ld + r0 ..]).
+template <bool KMAJOR, int ROWS, int NT>
 __device__ __forceinline__ void load_slab(double* s, const double* __restrict__ P, int64_t ld, int r0, int k0, int tid) {
+    constexpr int CHUNKS = ROWS * 8;  // 16-byte chunks in the slab
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        int id = tid + i * NTHREADS;  // 0..1023 16-byte chunks
+    for (int i = 0; i < CHUNKS / NT; ++i) {
+        int id = tid + i * NT;
         if (KMAJOR) {
             int r = id >> 3, c = id & 7;
             cp_async16(s + r * KC_LD + c * 2, P + (int64_t)(r0 + r) * ld + k0 + c * 2);
         } else {
-            int kr = id >> 6, c = id & 63;
-            cp_async16(s + kr * KS_LD + c * 2, P + (int64_t)(k0 + kr) * ld + r0 + c * 2);
+            constexpr int CPR = ROWS / 2;  // chunks per k-row
+            int kr = id / CPR, c = id % CPR;
+            cp_async16(s + kr * (ROWS + 4) + c * 2, P + (int64_t)(k0 + kr) * ld + r0 + c * 2);
         }
     }
 }
 
-template <bool A_KM, bool B_KM>
-__global__ void __launch_bounds__(NTHREADS, 1) dgemm_dmma_kernel(GemmArgs p) {
+__device__ __forceinline__ int mapped_pos(const GemmArgs& p, int col0) {
+    if (p.cyc_P <= 0) return col0;
+    const int bw = p.cyc_tpb * 128;  // block width in elements
+    const int lb = col0 / bw;
+    return ((lb + p.cyc_q0) * p.cyc_P + p.cyc_p) * bw + col0 % bw - p.cyc_row_base;
+}
+
+template <bool A_KM, bool B_KM, int TN>
+__global__ void __launch_bounds__(Cfg<TN>::NT, Cfg<TN>::MIN_CTAS) dgemm_dmma_kernel(GemmArgs p) {
+    using C_ = Cfg<TN>;
+    constexpr int NT = C_::NT, STAGES = C_::STAGES;
+    constexpr int KS_LDA = 128 + 4, KS_LDB = TN + 4;
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x;
     const int bn = blockIdx.x;
     const int bm = p.rev_rows ? (gridDim.y - 1 - blockIdx.y) : blockIdx.y;
-    const int row0 = bm * BM, col0 = bn * BN;
-    int gpos = col0;   // position of this column tile in global (block-cyclic) numbering, relative to cyc_row_base
-    if (p.cyc_P > 0) {
-        const int lb = bn / p.cyc_tpb;
-        gpos = (((lb + p.cyc_q0) * p.cyc_P + p.cyc_p) * p.cyc_tpb + bn % p.cyc_tpb) * BN - p.cyc_row_base;
-    }
+    const int row0 = bm * BM, col0 = bn * TN;
+    const int gpos = mapped_pos(p, col0);  // column position in global (block-cyclic) numbering
     const int brow0 = (p.cyc_P > 0 && !p.cyc_b_rows) ? col0 : gpos;  // offset of this column tile inside the B operand
-    if (p.lower_only && gpos > row0) return;
+    if (p.lower_only && gpos >= row0 + BM) return;                    // tile entirely above the diagonal
     const double* __restrict__ A = p.A + (int64_t)blockIdx.z * p.sA;
     const double* __restrict__ B = p.B + (int64_t)blockIdx.z * p.sB;
     double* C = p.C + (int64_t)blockIdx.z * p.sC;
 
-    int kbeg = (p.kb_mode == 1 ? row0 : (p.kb_mode == 2 ? col0 : (p.kb_mode == 3 ? gpos : 0))) + (int)(blockIdx.z * p.kb_batch) + p.kb_const;
+    int kbeg = (p.kb_mode == 1 ? row0 : (p.kb_mode == 2 ? (col0 / 128) * 128 : (p.kb_mode == 3 ? (gpos / 128) * 128 : 0))) +
+               (int)(blockIdx.z * p.kb_batch) + p.kb_const;
     if (kbeg < 0) kbeg = 0;
-    int kend = p.ke_mode == 1 ? row0 + BM : (p.ke_mode == 2 ? col0 + BN : p.K);
+    int kend = p.ke_mode == 1 ? row0 + BM : (p.ke_mode == 2 ? (col0 / 128) * 128 + 128 : p.K);
     if (kend > p.K) kend = p.K;
     const int nk = kend > kbeg ? (kend - kbeg) / BK : 0;
 
     const int warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int wm0 = (warp >> 2) * 64, wn0 = (warp & 3) * 32;
+    const int wm0 = (warp / C_::WN) * 64, wn0 = (warp % C_::WN) * 32;
 
     double acc[8][4][2];
 #pragma unroll
@@ -84,15 +106,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgemm_dmma_kernel(GemmArgs p) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    auto sA = [&](int st) { return smem + (st * 2 + 0) * OP_ELEMS; };
-    auto sB = [&](int st) { return smem + (st * 2 + 1) * OP_ELEMS; };
+    auto sA = [&](int st) { return smem + st * (C_::A_ELEMS + C_::B_ELEMS); };
+    auto sB = [&](int st) { return smem + st * (C_::A_ELEMS + C_::B_ELEMS) + C_::A_ELEMS; };
 
     // prologue: prefetch STAGES-1 slabs
 #pragma unroll
     for (int st = 0; st < STAGES - 1; ++st) {
         if (st < nk) {
-            load_slab<A_KM>(sA(st), A, p.lda, row0, kbeg + st * BK, tid);
-            load_slab<B_KM>(sB(st), B, p.ldb, brow0, kbeg + st * BK, tid);
+            load_slab<A_KM, 128, NT>(sA(st), A, p.lda, row0, kbeg + st * BK, tid);
+            load_slab<B_KM, TN, NT>(sB(st), B, p.ldb, brow0, kbeg + st * BK, tid);
         }
         cp_async_commit();
     }
@@ -104,8 +126,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgemm_dmma_kernel(GemmArgs p) {
             int nxt = kt + STAGES - 1;
             if (nxt < nk) {
                 int st = nxt % STAGES;
-                load_slab<A_KM>(sA(st), A, p.lda, row0, kbeg + nxt * BK, tid);
-                load_slab<B_KM>(sB(st), B, p.ldb, brow0, kbeg + nxt * BK, tid);
+                load_slab<A_KM, 128, NT>(sA(st), A, p.lda, row0, kbeg + nxt * BK, tid);
+                load_slab<B_KM, TN, NT>(sB(st), B, p.ldb, brow0, kbeg + nxt * BK, tid);
             }
             cp_async_commit();
         }
@@ -116,10 +138,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgemm_dmma_kernel(GemmArgs p) {
             double af[8], bf[4];
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-                af[i] = A_KM ? a_s[(wm0 + i * 8 + g) * KC_LD + kk + t] : a_s[(kk + t) * KS_LD + wm0 + i * 8 + g];
+                af[i] = A_KM ? a_s[(wm0 + i * 8 + g) * KC_LD + kk + t] : a_s[(kk + t) * KS_LDA + wm0 + i * 8 + g];
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                bf[j] = B_KM ? b_s[(wn0 + j * 8 + g) * KC_LD + kk + t] : b_s[(kk + t) * KS_LD + wn0 + j * 8 + g];
+                bf[j] = B_KM ? b_s[(wn0 + j * 8 + g) * KC_LD + kk + t] : b_s[(kk + t) * KS_LDB + wn0 + j * 8 + g];
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -128,7 +150,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgemm_dmma_kernel(GemmArgs p) {
     }
     cp_async_wait<0>();
     // all of this CTA's operand reads have landed before any of its stores: in-place use is safe when
-    // the operand tile the CTA reads is exactly its own output tile (TRSM leaves).
+    // the operand region the CTA reads is exactly its own output tile (TRSM leaves).
     __syncthreads();
 
     const double alpha = p.alpha, beta = p.beta;
@@ -152,23 +174,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgemm_dmma_kernel(GemmArgs p) {
     }
 }
 
-template <bool A_KM, bool B_KM>
+int host_mapped_pos(const GemmArgs& a, int col0) {
+    if (a.cyc_P <= 0) return col0;
+    const int bw = a.cyc_tpb * 128;
+    return ((col0 / bw + a.cyc_q0) * a.cyc_P + a.cyc_p) * bw + col0 % bw - a.cyc_row_base;
+}
+
+template <bool A_KM, bool B_KM, int TN>
 int launch_t(gpx_ctx* h, const GemmArgs& a) {
+    using C_ = Cfg<TN>;
     static bool configured = false;
     if (!configured) {
-        GPX_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<A_KM, B_KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        GPX_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<A_KM, B_KM, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM));
+        GPX_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<A_KM, B_KM, TN>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         configured = true;
     }
-    dim3 grid(a.N / BN, a.M / BM, a.batch > 0 ? a.batch : 1);
+    dim3 grid(a.N / TN, a.M / BM, a.batch > 0 ? a.batch : 1);
     if (h->timing_on) {  // flops the launch really executes (tile-granular k ranges)
         double ksum = 0.0;
         for (int bm = 0; bm < (int)grid.y; ++bm)
             for (int bn = 0; bn < (int)grid.x; ++bn) {
-                int br = bn * BN;
-                if (a.cyc_P > 0) br = (((bn / a.cyc_tpb + a.cyc_q0) * a.cyc_P + a.cyc_p) * a.cyc_tpb + bn % a.cyc_tpb) * BN - a.cyc_row_base;
-                if (a.lower_only && br > bm * BM) continue;
-                int kb = a.kb_mode == 1 ? bm * BM : (a.kb_mode == 2 ? bn * BN : (a.kb_mode == 3 ? br : 0));
-                int ke = a.ke_mode == 1 ? bm * BM + BM : (a.ke_mode == 2 ? bn * BN + BN : a.K);
+                const int col0 = bn * TN;
+                const int gp = host_mapped_pos(a, col0);
+                if (a.lower_only && gp >= bm * BM + BM) continue;
+                int kb = a.kb_mode == 1 ? bm * BM : (a.kb_mode == 2 ? (col0 / 128) * 128 : (a.kb_mode == 3 ? (gp / 128) * 128 : 0));
+                int ke = a.ke_mode == 1 ? bm * BM + BM : (a.ke_mode == 2 ? (col0 / 128) * 128 + 128 : a.K);
                 if (ke > a.K) ke = a.K;
                 for (int z = 0; z < (int)grid.z; ++z) {
                     int kbz = kb + (int)(z * a.kb_batch) + a.kb_const;
@@ -176,25 +206,42 @@ int launch_t(gpx_ctx* h, const GemmArgs& a) {
                     if (ke > kbz) ksum += (double)(ke - kbz);
                 }
             }
-        gpx_timing_gemm_begin(h, 2.0 * BM * BN * ksum);
+        gpx_timing_gemm_begin(h, 2.0 * BM * TN * ksum);
     }
-    dgemm_dmma_kernel<A_KM, B_KM><<<grid, NTHREADS, SMEM_BYTES, h->stream>>>(a);
+    dgemm_dmma_kernel<A_KM, B_KM, TN><<<grid, C_::NT, C_::SMEM, h->stream>>>(a);
     GPX_CHECK_LAUNCH(h);
     gpx_timing_gemm_end(h);
     return 0;
+}
+
+template <int TN>
+int dispatch(gpx_ctx* h, const GemmArgs& a) {
+    if (a.a_kmajor && a.b_kmajor) return launch_t<true, true, TN>(h, a);
+    if (a.a_kmajor && !a.b_kmajor) return launch_t<true, false, TN>(h, a);
+    if (!a.a_kmajor && a.b_kmajor) return launch_t<false, true, TN>(h, a);
+    return launch_t<false, false, TN>(h, a);
+}
+
+int default_tn() {
+    static int tn = 0;
+    if (tn == 0) {
+        const char* e = getenv("GPX_GEMM_TN");
+        tn = (e && atoi(e) == 128) ? 128 : 64;
+    }
+    return tn;
 }
 
 }  // namespace
 
 int gpx_gemm_launch(gpx_ctx* h, const GemmArgs& a) {
     if (a.M <= 0 || a.N <= 0) return 0;
-    GPX_REQUIRE(a.M % BM == 0 && a.N % BN == 0 && a.K % BK == 0, 2);
+    GPX_REQUIRE(a.M % BM == 0 && a.N % 128 == 0 && a.K % BK == 0, 2);
     GPX_REQUIRE(a.lda % 2 == 0 && a.ldb % 2 == 0 && a.ldc % 2 == 0, 3);
     GPX_REQUIRE(((uintptr_t)a.A % 16) == 0 && ((uintptr_t)a.B % 16) == 0 && ((uintptr_t)a.C % 16) == 0, 4);
-    if (a.a_kmajor && a.b_kmajor) return launch_t<true, true>(h, a);
-    if (a.a_kmajor && !a.b_kmajor) return launch_t<true, false>(h, a);
-    if (!a.a_kmajor && a.b_kmajor) return launch_t<false, true>(h, a);
-    return launch_t<false, false>(h, a);
+    // a right-TRSM leaf updates a 128-wide row block in place: one CTA must own the whole block
+    const bool inplace_rows = (a.C == a.A) && a.a_kmajor;
+    if (inplace_rows || default_tn() == 128) return dispatch<128>(h, a);
+    return dispatch<64>(h, a);
 }
 
 extern "C" int gpx_gemm(gpx_handle h, int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K, double alpha,
