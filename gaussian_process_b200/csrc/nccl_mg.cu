@@ -136,26 +136,36 @@ int64_t first_local_block_after(const MgRank& r, int64_t j) {  // smallest q wit
     return (j - r.p) / r.P + 1;
 }
 
-// local block columns of K^-1 = X^T X (rows >= column block), X replicated in Xall[rank][npad][wloc]
+// Xall[rank][npad][wloc] (rank-major, as all-gathered) -> Xg[block][npad][nb] in GLOBAL block order (panel-major);
+// only rows at/below each block's diagonal are copied (the rest of X is zero and never read).  Xg reuses Lfull.
+int reorder_X(MgRank& r) {
+    for (int64_t i = 0; i < r.nblk; ++i) {
+        const int src = (int)(i % r.P);
+        const int64_t q = i / r.P, r0 = i * r.nb;
+        const double* from = r.Xall + (size_t)src * r.npad * r.wloc + r0 * r.wloc + q * r.nb;
+        double* to = r.Lfull + (size_t)i * r.npad * r.nb + r0 * r.nb;
+        GPX_CUDA(cudaMemcpy2DAsync(to, r.nb * sizeof(double), from, r.wloc * sizeof(double), r.nb * sizeof(double),
+                                   r.npad - r0, cudaMemcpyDeviceToDevice, r.h->stream));
+    }
+    return 0;
+}
+
+// local block columns of K^-1 = X^T X (rows >= column block): one batched triangular DMMA launch per owned column
+// block j, batch index z <-> row block i = j + z, all reading the panel-major replicated X (Xg = Lfull buffer).
 int lauum_local(MgRank& r) {
+    const double* Xg = r.Lfull;
+    const int64_t pstride = r.npad * r.nb;   // elements per panel
     for (int64_t q = 0; q < r.nloc; ++q) {
         const int64_t j = q * r.P + r.p, kbase = j * r.nb;
-        const double* Bop = r.Xall + (size_t)r.p * r.npad * r.wloc + kbase * r.wloc + q * r.nb;
-        for (int src = 0; src < r.P; ++src) {
-            // row blocks i = qi*P + src with i >= j
-            int64_t qi0 = (j <= src) ? 0 : (j - src + r.P - 1) / r.P;
-            if (qi0 >= r.nloc) continue;
-            const int64_t i0 = qi0 * r.P + src;
-            GemmArgs a{};
-            a.alpha = 1.0; a.beta = 0.0;
-            a.batch = (int)(r.nloc - qi0);
-            a.A = r.Xall + (size_t)src * r.npad * r.wloc + kbase * r.wloc + qi0 * r.nb; a.lda = r.wloc; a.a_kmajor = 0; a.sA = r.nb;
-            a.B = Bop; a.ldb = r.wloc; a.b_kmajor = 0; a.sB = 0;
-            a.C = r.Kloc + (i0 * r.nb) * r.wloc + q * r.nb; a.ldc = r.wloc; a.sC = (int64_t)r.P * r.nb * r.wloc;
-            a.M = r.nb; a.N = r.nb; a.K = (int)(r.npad - kbase);
-            a.kb_mode = 1; a.kb_batch = (int64_t)r.P * r.nb; a.kb_const = (int)(i0 * r.nb - kbase);
-            GPX_TRY(gpx_gemm_launch(r.h, a));
-        }
+        GemmArgs a{};
+        a.alpha = 1.0; a.beta = 0.0;
+        a.batch = (int)(r.nblk - j);
+        a.A = Xg + j * pstride + kbase * r.nb; a.lda = r.nb; a.a_kmajor = 0; a.sA = pstride;
+        a.B = a.A; a.ldb = r.nb; a.b_kmajor = 0; a.sB = 0;
+        a.C = r.Kloc + kbase * r.wloc + q * r.nb; a.ldc = r.wloc; a.sC = (int64_t)r.nb * r.wloc;
+        a.M = r.nb; a.N = r.nb; a.K = (int)(r.npad - kbase);
+        a.kb_mode = 1; a.kb_batch = r.nb; a.kb_const = 0;
+        GPX_TRY(gpx_gemm_launch(r.h, a));
     }
     return 0;
 }
@@ -336,6 +346,7 @@ extern "C" int gpx_mg_fit_grad(gpx_handle h, int kind, const double* X, int64_t 
         GPX_NCCL(g_nccl.AllGather(r.Xall + (size_t)r.p * cnt, r.Xall, cnt, NCCL_F64, (ncclComm_p)h->nccl_comm, S));
     }
     gpx_phase_mark(h, GPX_PH_LAUUM);
+    GPX_TRY(reorder_X(r));
     GPX_TRY(lauum_local(r));
     gpx_phase_mark(h, GPX_PH_GRAD);
     GPX_CUDA(cudaMemsetAsync(grad, 0, ntheta * sizeof(double), S));
@@ -388,6 +399,7 @@ extern "C" int gpx_mg_emulate_fit_grad(gpx_handle h, int P, int kind, const doub
                                          cudaMemcpyDeviceToDevice, S));
     GPX_CUDA(cudaMemsetAsync(grad, 0, ntheta * sizeof(double), S));
     for (int p = 0; p < P; ++p) {
+        GPX_TRY(reorder_X(R[p]));
         GPX_TRY(lauum_local(R[p]));
         GPX_TRY(grad_local(R[p], kind, X, D, theta_host, ntheta, alpha, grad, h->d_theta));  // sums over ranks = all-reduce
     }
