@@ -65,4 +65,4 @@ def test_two_rank_nccl_job():
            "--master-port", "29533", os.path.join(ROOT, "tools", "mg_check.py"), "--npoints", "3000", "--block", "256"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert "MG_CHECK_OK" in out.stdout
+    assert "MG_CHECK_OK" in out.stdout and "MG_SHARD_OK" in out.stdout

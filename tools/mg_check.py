@@ -35,6 +35,25 @@ def main():
         print("world=%d lml rel %.2e grad rel %.2e alpha rel %.2e" % (dist.get_world_size(), e1, e2, e3))
         assert e1 < 1e-8 and e2 < 1e-7 and e3 < 1e-7
         print("MG_CHECK_OK")
+    # ---- sharded prediction (test points split over ranks) and class-sharded multiclass Laplace
+    from gaussian_process_b200.distributed import multiclass_newton_sharded, predict_sharded
+    from gaussian_process_b200.engine import padded
+    Xc, yc, Xs = O.synth_c1(200, 333)
+    fit = eng.fit(COV_SE, Xc, yc, [1.0, 1.0], 5e-4)
+    mu, var = predict_sharded(eng, fit, Xs)
+    np.random.seed(0)
+    mu_o, sd_o, _ = O.regression_prediction(Xc, Xs, yc, 'rbf', 1, 1)
+    assert np.max(np.abs(mu - mu_o)) < 1e-8 * np.max(np.abs(mu_o)) and np.max(np.abs(var - sd_o ** 2)) < 1e-8 * np.max(sd_o ** 2)
+    Xm, labels, ym, Xt, tl = O.synth_c4(n=300, C=5, D=6, n_test=10)
+    Xd = eng.to_device(Xm)
+    Kd = eng.cov(COV_SE, Xd, Xd, [1.0, 1.0], same_x=True)
+    model = multiclass_newton_sharded(eng, Kd, ym, 5, 300, tolerance=1e-9)
+    p_o, f_o, it_o = O.multi_training_newton(O.rbf_kernel(Xm, Xm, 1, 1), ym, 5, 300, tolerance=1e-9)
+    ef = float(np.max(np.abs(eng.to_host(model.f) - f_o)) / np.max(np.abs(f_o)))
+    assert ef < 1e-6, ef
+    if dist.get_rank() == 0:
+        print("sharded prediction ok; class-sharded multiclass Laplace rel err %.2e (classes on rank 0: %s)" % (ef, model.classes))
+        print("MG_SHARD_OK")
     dist.barrier()
     dist.destroy_process_group()
 
