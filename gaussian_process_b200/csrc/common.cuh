@@ -30,6 +30,8 @@ enum { GPX_PH_COV = 0, GPX_PH_POTRF = 1, GPX_PH_SOLVE = 2, GPX_PH_TRTRI = 3, GPX
        GPX_PH_END = 6, GPX_NPHASES = 8 };
 void gpx_timing_gemm_begin(gpx_ctx* h, double flops_exec);
 void gpx_timing_gemm_end(gpx_ctx* h);
+void gpx_timing_leaf_begin(gpx_ctx* h);
+void gpx_timing_leaf_end(gpx_ctx* h);
 void gpx_phase_mark(gpx_ctx* h, int phase);
 void gpx_timing_destroy(gpx_ctx* h);
 

@@ -15,85 +15,207 @@
 namespace {
 
 constexpr int LT = 128;          // leaf size
-constexpr int LLD = LT + 1;      // padded smem leading dimension
-constexpr int LEAF_THREADS = 512;
+constexpr int LB = 4;            // register block edge: thread (bi,bj) owns the 4x4 block of the lower triangle
+constexpr int NBK = LT / LB;     // 32 block rows -> 528 lower blocks
+constexpr int LLD = LT + 4;      // smem leading dimension (rows stay 16-byte aligned)
+constexpr int LEAF_THREADS = 544;
 constexpr int LEAF_SMEM = (LT * LLD + LT) * (int)sizeof(double);
 
-// One CTA factors one 128x128 diagonal block in shared memory.
-//  S (lower+diag) <- L ; S (strict upper) <- (L^-1)^T ; dinv_diag <- 1/L_ii
+// One CTA factors one 128x128 diagonal block and inverts the factor.  The whole lower triangle lives in
+// REGISTERS (one 4x4 block per thread); shared memory only carries the finished panel values:
+//   step p (32 steps): thread (p,p) factors its 4x4 block and inverts it | panel threads (i,p) multiply by
+//   L_pp^-T | every thread (i,j>p) applies the rank-4 update from shared memory.  2 barriers per step.
+// Then X = L^-1 right-looking over block rows (1 barrier per step), X stored transposed in the unused upper
+// triangle of the same smem tile:  S(lower+diag) = L, S(strict upper) = X^T, dd = diag(X).
 //  A tile <- L (upper zeroed) ; Dinv tile <- L^-1 (upper zeroed)
 // info: first failing pivot (global 1-based index) is recorded once.
 __global__ void __launch_bounds__(LEAF_THREADS, 1)
 potrf_leaf_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ Dinv, int* info, int global_off,
                   int64_t strideA, int64_t strideD) {
-    extern __shared__ double sm[];
+    extern __shared__ __align__(16) double sm[];
+    __shared__ int fail_col;
     double* S = sm;
     double* dd = sm + LT * LLD;
     A += (int64_t)blockIdx.x * strideA;
     Dinv += (int64_t)blockIdx.x * strideD;
     global_off += blockIdx.x * LT;
     const int tid = threadIdx.x;
-    // load lower triangle (incl. diagonal)
-    for (int idx = tid; idx < LT * LT; idx += LEAF_THREADS) {
-        int i = idx >> 7, j = idx & 127;
-        S[i * LLD + j] = (j <= i) ? A[(int64_t)i * lda + j] : 0.0;
+    int bi = -1, bj = -1;
+    if (tid < NBK * (NBK + 1) / 2) {
+        bi = (int)((sqrtf(8.f * tid + 1.f) - 1.f) * 0.5f);
+        while (bi * (bi + 1) / 2 > tid) --bi;
+        while ((bi + 1) * (bi + 2) / 2 <= tid) ++bi;
+        bj = tid - bi * (bi + 1) / 2;
     }
-    __syncthreads();
-    // right-looking, un-normalised columns: after step j, S[i][k] -= S[i][j] S[k][j] / S[j][j]
-    const int tx = tid & 31, ty = tid >> 5;  // 32 x 16
-    bool failed = false;
-    for (int j = 0; j < LT; ++j) {
-        const double d = S[j * LLD + j];
-        if (!(d > 0.0)) {  // also catches NaN
-            if (tid == 0) atomicCAS(info, 0, global_off + j + 1);
-            failed = true;
-            break;
+    const bool active = bi >= 0;
+    double a[LB][LB];
+    if (active) {
+#pragma unroll
+        for (int r = 0; r < LB; ++r) {
+            const double2* src = reinterpret_cast<const double2*>(A + (int64_t)(LB * bi + r) * lda + LB * bj);
+            double2 v0 = src[0], v1 = src[1];
+            a[r][0] = v0.x; a[r][1] = v0.y; a[r][2] = v1.x; a[r][3] = v1.y;
         }
-        const double rd = 1.0 / d;
-        for (int i = j + 1 + ty; i < LT; i += 16) {
-            const double lij = S[i * LLD + j] * rd;
-            for (int k = j + 1 + tx; k <= i; k += 32) S[i * LLD + k] -= lij * S[k * LLD + j];
+    }
+    if (tid == 0) fail_col = -1;
+    __syncthreads();
+
+    for (int p = 0; p < NBK; ++p) {
+        if (active && bi == p && bj == p) {   // ---- 4x4 Cholesky + inverse of the diagonal block, in registers
+            double l[LB][LB], x[LB][LB];
+            int bad = -1;
+#pragma unroll
+            for (int c = 0; c < LB; ++c) {
+                double d = a[c][c];
+#pragma unroll
+                for (int m = 0; m < c; ++m) d -= l[c][m] * l[c][m];
+                if (!(d > 0.0) && bad < 0) bad = c;
+                const double lc = sqrt(d);
+                const double rc = 1.0 / lc;
+                l[c][c] = lc;
+                x[c][c] = rc;
+#pragma unroll
+                for (int r = c + 1; r < LB; ++r) {
+                    double v = a[r][c];
+#pragma unroll
+                    for (int m = 0; m < c; ++m) v -= l[r][m] * l[c][m];
+                    l[r][c] = v * rc;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < LB; ++c)
+#pragma unroll
+                for (int r = c + 1; r < LB; ++r) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int m = c; m < r; ++m) v += l[r][m] * x[m][c];
+                    x[r][c] = -v * x[r][r];
+                }
+            if (bad >= 0) fail_col = LB * p + bad;
+#pragma unroll
+            for (int r = 0; r < LB; ++r) {
+                dd[LB * p + r] = x[r][r];
+#pragma unroll
+                for (int c = 0; c <= r; ++c) S[(LB * p + r) * LLD + LB * p + c] = l[r][c];
+#pragma unroll
+                for (int c = 0; c < r; ++c) S[(LB * p + c) * LLD + LB * p + r] = x[r][c];   // X_pp^T above the diagonal
+            }
         }
         __syncthreads();
+        if (fail_col >= 0) break;
+        if (active && bj == p && bi > p) {    // ---- panel: A_ip <- A_ip * L_pp^-T = A_ip * X_pp^T
+            double x[LB][LB];
+#pragma unroll
+            for (int r = 0; r < LB; ++r) {
+                x[r][r] = dd[LB * p + r];
+#pragma unroll
+                for (int c = 0; c < r; ++c) x[r][c] = S[(LB * p + c) * LLD + LB * p + r];
+            }
+#pragma unroll
+            for (int r = 0; r < LB; ++r) {
+                double o[LB];
+#pragma unroll
+                for (int c = 0; c < LB; ++c) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int m = 0; m <= c; ++m) v += a[r][m] * x[c][m];
+                    o[c] = v;
+                }
+                double2* dst = reinterpret_cast<double2*>(S + (LB * bi + r) * LLD + LB * p);
+                dst[0] = make_double2(o[0], o[1]);
+                dst[1] = make_double2(o[2], o[3]);
+            }
+        }
+        __syncthreads();
+        if (active && bj > p) {               // ---- rank-4 update of the trailing blocks (registers)
+            double li[LB][LB], lj[LB][LB];
+#pragma unroll
+            for (int r = 0; r < LB; ++r) {
+                const double2* pi_ = reinterpret_cast<const double2*>(S + (LB * bi + r) * LLD + LB * p);
+                const double2* pj_ = reinterpret_cast<const double2*>(S + (LB * bj + r) * LLD + LB * p);
+                double2 u0 = pi_[0], u1 = pi_[1], w0 = pj_[0], w1 = pj_[1];
+                li[r][0] = u0.x; li[r][1] = u0.y; li[r][2] = u1.x; li[r][3] = u1.y;
+                lj[r][0] = w0.x; lj[r][1] = w0.y; lj[r][2] = w1.x; lj[r][3] = w1.y;
+            }
+#pragma unroll
+            for (int r = 0; r < LB; ++r)
+#pragma unroll
+                for (int c = 0; c < LB; ++c)
+#pragma unroll
+                    for (int m = 0; m < LB; ++m) a[r][c] -= li[r][m] * lj[c][m];
+        }
     }
-    if (failed) {
-        // poison the outputs so downstream results are visibly invalid; host reads `info`
+    if (fail_col >= 0) {
+        if (tid == 0) atomicCAS(info, 0, global_off + fail_col + 1);
+        // poison the outputs so downstream results are visibly invalid; the host reads `info`
+        const double qnan = __longlong_as_double(0x7ff8000000000000LL);
         for (int idx = tid; idx < LT * LT; idx += LEAF_THREADS) {
             int i = idx >> 7, j = idx & 127;
-            A[(int64_t)i * lda + j] = (j <= i) ? __longlong_as_double(0x7ff8000000000000LL) : 0.0;
-            Dinv[idx] = (j <= i) ? __longlong_as_double(0x7ff8000000000000LL) : 0.0;
+            A[(int64_t)i * lda + j] = (j <= i) ? qnan : 0.0;
+            Dinv[idx] = (j <= i) ? qnan : 0.0;
         }
         return;
     }
-    // normalise: L[j][j] = sqrt(d_j), L[i][j] = S[i][j] / sqrt(d_j)
-    if (tid < LT) dd[tid] = sqrt(S[tid * LLD + tid]);
-    __syncthreads();
-    for (int idx = tid; idx < LT * LT; idx += LEAF_THREADS) {
-        int i = idx >> 7, j = idx & 127;
-        if (j < i) S[i * LLD + j] /= dd[j];
-    }
-    __syncthreads();
-    if (tid < LT) {
-        S[tid * LLD + tid] = dd[tid];
-        dd[tid] = 1.0 / dd[tid];
-    }
-    __syncthreads();
-    // inverse: column c of X = L^-1 by forward substitution, 4 threads per column (same warp)
-    // X[i][c] is kept at S[c][i] (strict upper), X[c][c] = dd[c].
-    {
-        const int c = tid >> 2, q = tid & 3;
-        for (int i = 1; i < LT; ++i) {  // uniform trip count; columns with c >= i idle
-            double part = 0.0;
-            if (c < i) {
-                for (int k = c + q; k < i; k += 4) {
-                    const double xk = (k == c) ? dd[c] : S[c * LLD + k];
-                    part += S[i * LLD + k] * xk;
-                }
+
+    // ---- X = L^-1, right-looking over block rows k: acc_ij = sum_{k} L_ik X_kj ; X_ij = -X_ii acc_ij
+    double acc[LB][LB];
+#pragma unroll
+    for (int r = 0; r < LB; ++r)
+#pragma unroll
+        for (int c = 0; c < LB; ++c) acc[r][c] = 0.0;
+    for (int k = 0; k < NBK; ++k) {
+        if (active && bi == k && bj < k) {    // finalise X_kj and publish it (transposed, above the diagonal)
+            double x[LB][LB];
+#pragma unroll
+            for (int r = 0; r < LB; ++r) {
+                x[r][r] = dd[LB * k + r];
+#pragma unroll
+                for (int c = 0; c < r; ++c) x[r][c] = S[(LB * k + c) * LLD + LB * k + r];
             }
-            part += __shfl_xor_sync(0xffffffffu, part, 1);
-            part += __shfl_xor_sync(0xffffffffu, part, 2);
-            if (c < i && q == 0) S[c * LLD + i] = -part * dd[i];
-            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < LB; ++c) {
+                double o[LB];
+#pragma unroll
+                for (int r = 0; r < LB; ++r) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int m = 0; m <= r; ++m) v += x[r][m] * acc[m][c];
+                    o[r] = -v;
+                }
+                double2* dst = reinterpret_cast<double2*>(S + (LB * bj + c) * LLD + LB * k);
+                dst[0] = make_double2(o[0], o[1]);
+                dst[1] = make_double2(o[2], o[3]);
+            }
+        }
+        __syncthreads();
+        if (active && bi > k && bj <= k) {    // acc_ij += L_ik X_kj
+            double li[LB][LB], xt[LB][LB];     // xt[c][m] = X_kj[m][c]
+#pragma unroll
+            for (int r = 0; r < LB; ++r) {
+                const double2* pi_ = reinterpret_cast<const double2*>(S + (LB * bi + r) * LLD + LB * k);
+                double2 u0 = pi_[0], u1 = pi_[1];
+                li[r][0] = u0.x; li[r][1] = u0.y; li[r][2] = u1.x; li[r][3] = u1.y;
+            }
+            if (bj < k) {
+#pragma unroll
+                for (int c = 0; c < LB; ++c) {
+                    const double2* px = reinterpret_cast<const double2*>(S + (LB * bj + c) * LLD + LB * k);
+                    double2 u0 = px[0], u1 = px[1];
+                    xt[c][0] = u0.x; xt[c][1] = u0.y; xt[c][2] = u1.x; xt[c][3] = u1.y;
+                }
+            } else {  // bj == k: X_kk (lower triangular)
+#pragma unroll
+                for (int c = 0; c < LB; ++c)
+#pragma unroll
+                    for (int m = 0; m < LB; ++m)
+                        xt[c][m] = (m == c) ? dd[LB * k + c] : (m > c ? S[(LB * k + c) * LLD + LB * k + m] : 0.0);
+            }
+#pragma unroll
+            for (int r = 0; r < LB; ++r)
+#pragma unroll
+                for (int c = 0; c < LB; ++c)
+#pragma unroll
+                    for (int m = 0; m < LB; ++m) acc[r][c] += li[r][m] * xt[c][m];
         }
     }
     __syncthreads();
@@ -122,8 +244,10 @@ int leaf(gpx_ctx* h, double* A, int64_t lda, double* dinv_tile, int goff, int ba
         GPX_CUDA(cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM));
         configured = true;
     }
+    gpx_timing_leaf_begin(h);
     potrf_leaf_kernel<<<batch, LEAF_THREADS, LEAF_SMEM, h->stream>>>(A, lda, dinv_tile, h->d_info, goff, strideA, strideD);
     GPX_CHECK_LAUNCH(h);
+    gpx_timing_leaf_end(h);
     return 0;
 }
 

@@ -7,6 +7,7 @@ struct gpx_timing {
     std::vector<cudaEvent_t> pool;      // reusable events
     size_t used = 0;
     std::vector<std::pair<size_t, size_t>> gemm_pairs;   // (start,end) event indices
+    std::vector<std::pair<size_t, size_t>> leaf_pairs;   // potrf leaf launches
     double gemm_flops_exec = 0.0;       // flops the kernel actually executes (tile-granular k ranges)
     std::vector<std::pair<int, size_t>> marks;            // (phase id, event index)
 };
@@ -40,6 +41,22 @@ void gpx_timing_gemm_end(gpx_ctx* h) {
     t->gemm_pairs.back().second = i1;
 }
 
+void gpx_timing_leaf_begin(gpx_ctx* h) {
+    if (!h->timing_on) return;
+    gpx_timing* t = (gpx_timing*)h->timing;
+    size_t i0;
+    cudaEventRecord(next_event(t, &i0), h->stream);
+    t->leaf_pairs.push_back({i0, (size_t)-1});
+}
+
+void gpx_timing_leaf_end(gpx_ctx* h) {
+    if (!h->timing_on) return;
+    gpx_timing* t = (gpx_timing*)h->timing;
+    size_t i1;
+    cudaEventRecord(next_event(t, &i1), h->stream);
+    t->leaf_pairs.back().second = i1;
+}
+
 void gpx_phase_mark(gpx_ctx* h, int phase) {
     if (!h->timing_on) return;
     gpx_timing* t = (gpx_timing*)h->timing;
@@ -55,6 +72,7 @@ extern "C" int gpx_timing_enable(gpx_handle h, int on) {
     gpx_timing* t = (gpx_timing*)h->timing;
     t->used = 0;
     t->gemm_pairs.clear();
+    t->leaf_pairs.clear();
     t->marks.clear();
     t->gemm_flops_exec = 0.0;
     h->timing_on = on ? 1 : 0;
@@ -62,7 +80,8 @@ extern "C" int gpx_timing_enable(gpx_handle h, int on) {
 }
 
 // out[0] = total DMMA-GEMM kernel ms, out[1] = #GEMM launches, out[2] = flops executed by those launches,
-// out[3 + p] = ms spent in phase p (time from mark p to the next mark), p < GPX_NPHASES.
+// out[3 + p] = ms spent in phase p (time from mark p to the next mark), p < GPX_NPHASES;
+// out[11] = potrf-leaf kernel ms, out[12] = #leaf launches (when nout >= 13).
 extern "C" int gpx_timing_collect(gpx_handle h, double* out, int nout) {
     GPX_REQUIRE(h != nullptr && h->timing != nullptr, 1);
     GPX_REQUIRE(nout >= 3 + GPX_NPHASES, 3);
@@ -74,6 +93,15 @@ extern "C" int gpx_timing_collect(gpx_handle h, double* out, int nout) {
         float ms = 0.f;
         GPX_CUDA(cudaEventElapsedTime(&ms, t->pool[pr.first], t->pool[pr.second]));
         out[0] += ms;
+    }
+    if (nout >= 3 + GPX_NPHASES + 2) {
+        for (auto& pr : t->leaf_pairs) {
+            if (pr.second == (size_t)-1) continue;
+            float ms = 0.f;
+            GPX_CUDA(cudaEventElapsedTime(&ms, t->pool[pr.first], t->pool[pr.second]));
+            out[3 + GPX_NPHASES] += ms;
+        }
+        out[3 + GPX_NPHASES + 1] = (double)t->leaf_pairs.size();
     }
     out[1] = (double)t->gemm_pairs.size();
     out[2] = t->gemm_flops_exec;
