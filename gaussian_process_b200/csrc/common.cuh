@@ -91,6 +91,7 @@ struct GemmArgs {
     int cyc_b_rows;             // 1: the mapped position is also B's row offset (trailing update); 0: B uses the local column
 };
 int gpx_gemm_launch(gpx_ctx* h, const GemmArgs& a);
+int gpx_gemm_tma_try_launch(gpx_ctx* h, const GemmArgs& a, double flops_exec);
 
 int gpx_lml_grad_block(gpx_ctx* h, int kind, const double* X, int64_t n, int D, const double* theta_host, int ntheta,
                        const double* Kinv, int64_t ldk, const double* alpha, double* grad, int64_t rows, int64_t cols, int rg0,

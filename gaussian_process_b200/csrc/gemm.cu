@@ -180,6 +180,27 @@ int host_mapped_pos(const GemmArgs& a, int col0) {
     return ((col0 / bw + a.cyc_q0) * a.cyc_P + a.cyc_p) * bw + col0 % bw - a.cyc_row_base;
 }
 
+// flops a launch really executes (tile-granular k ranges), for the instrumentation
+double exec_flops(const GemmArgs& a, int TN) {
+    const int gx = a.N / TN, gy = a.M / BM, gz = a.batch > 0 ? a.batch : 1;
+    double ksum = 0.0;
+    for (int bm = 0; bm < gy; ++bm)
+        for (int bn = 0; bn < gx; ++bn) {
+            const int col0 = bn * TN;
+            const int gp = host_mapped_pos(a, col0);
+            if (a.lower_only && gp >= bm * BM + BM) continue;
+            int kb = a.kb_mode == 1 ? bm * BM : (a.kb_mode == 2 ? (col0 / 128) * 128 : (a.kb_mode == 3 ? (gp / 128) * 128 : 0));
+            int ke = a.ke_mode == 1 ? bm * BM + BM : (a.ke_mode == 2 ? (col0 / 128) * 128 + 128 : a.K);
+            if (ke > a.K) ke = a.K;
+            for (int z = 0; z < gz; ++z) {
+                int kbz = kb + (int)(z * a.kb_batch) + a.kb_const;
+                if (kbz < 0) kbz = 0;
+                if (ke > kbz) ksum += (double)(ke - kbz);
+            }
+        }
+    return 2.0 * BM * TN * ksum;
+}
+
 template <bool A_KM, bool B_KM, int TN>
 int launch_t(gpx_ctx* h, const GemmArgs& a) {
     using C_ = Cfg<TN>;
@@ -190,24 +211,7 @@ int launch_t(gpx_ctx* h, const GemmArgs& a) {
         configured = true;
     }
     dim3 grid(a.N / TN, a.M / BM, a.batch > 0 ? a.batch : 1);
-    if (h->timing_on) {  // flops the launch really executes (tile-granular k ranges)
-        double ksum = 0.0;
-        for (int bm = 0; bm < (int)grid.y; ++bm)
-            for (int bn = 0; bn < (int)grid.x; ++bn) {
-                const int col0 = bn * TN;
-                const int gp = host_mapped_pos(a, col0);
-                if (a.lower_only && gp >= bm * BM + BM) continue;
-                int kb = a.kb_mode == 1 ? bm * BM : (a.kb_mode == 2 ? (col0 / 128) * 128 : (a.kb_mode == 3 ? (gp / 128) * 128 : 0));
-                int ke = a.ke_mode == 1 ? bm * BM + BM : (a.ke_mode == 2 ? (col0 / 128) * 128 + 128 : a.K);
-                if (ke > a.K) ke = a.K;
-                for (int z = 0; z < (int)grid.z; ++z) {
-                    int kbz = kb + (int)(z * a.kb_batch) + a.kb_const;
-                    if (kbz < 0) kbz = 0;
-                    if (ke > kbz) ksum += (double)(ke - kbz);
-                }
-            }
-        gpx_timing_gemm_begin(h, 2.0 * BM * TN * ksum);
-    }
+    if (h->timing_on) gpx_timing_gemm_begin(h, exec_flops(a, TN));
     dgemm_dmma_kernel<A_KM, B_KM, TN><<<grid, C_::NT, C_::SMEM, h->stream>>>(a);
     GPX_CHECK_LAUNCH(h);
     gpx_timing_gemm_end(h);
@@ -241,6 +245,10 @@ int gpx_gemm_launch(gpx_ctx* h, const GemmArgs& a) {
     // a right-TRSM leaf updates a 128-wide row block in place: one CTA must own the whole block
     const bool inplace_rows = (a.C == a.A) && a.a_kmajor;
     if (inplace_rows || default_tn() == 128) return dispatch<128>(h, a);
+    {   // k-major x k-major (trailing update / TRSM update): TMA-fed kernel when available
+        const int r = gpx_gemm_tma_try_launch(h, a, h->timing_on ? exec_flops(a, 64) : 0.0);
+        if (r != 0) return r < 0 ? r : 0;
+    }
     return dispatch<64>(h, a);
 }
 
