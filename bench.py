@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--cpu-sample-n", type=int, default=4096, help="size of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--block", dest="nb", type=int, default=512, help="block-cyclic block width of the multi-GPU path")
+    ap.add_argument("--block", dest="nb", type=int, default=256, help="block-cyclic block width of the multi-GPU path")
     ap.add_argument("--mg", action="store_true", help="use the block-cyclic multi-GPU driver even at world size 1")
     return ap.parse_args()
 

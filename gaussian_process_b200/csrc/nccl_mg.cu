@@ -214,6 +214,27 @@ int solve_lml(MgRank& r, const double* y, double* alpha, double* out3) {
     return gpx_lml(h, r.Lfull, r.n, r.npad, y, alpha, out3);
 }
 
+// alpha = X^T (X y) from the replicated, panel-major inverse factor X = L^-1 (Xg in the Lfull buffer): two sweeps of
+// HBM-bound GEMVs with no sequential dependency (the reference's CO2 path forms alpha the same way, CO2...:144-145).
+// `diag` holds diag(L) saved before the factor buffer was recycled; out3 as gpx_lml.
+int solve_lml_from_inverse(MgRank& r, const double* y, double* alpha, double* tmp, const double* diag, double* out3) {
+    gpx_ctx* h = r.h;
+    const double* Xg = r.Lfull;
+    const int64_t pstride = r.npad * r.nb;
+    GPX_CUDA(cudaMemsetAsync(tmp, 0, r.npad * sizeof(double), h->stream));
+    GPX_CUDA(cudaMemsetAsync(alpha, 0, r.npad * sizeof(double), h->stream));
+    GPX_CUDA(cudaMemcpyAsync(alpha, y, r.n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));   // padded y
+    for (int64_t j = 0; j < r.nblk; ++j) {      // tmp = X y  (panel j contributes to rows >= j*nb)
+        const int64_t r0 = j * r.nb;
+        GPX_TRY(gpx_gemv(h, 0, r.npad - r0, r.nb, 1.0, Xg + j * pstride + r0 * r.nb, r.nb, alpha + r0, 1.0, tmp + r0));
+    }
+    for (int64_t j = 0; j < r.nblk; ++j) {      // alpha_j = X_j^T tmp
+        const int64_t r0 = j * r.nb;
+        GPX_TRY(gpx_gemv(h, 1, r.npad - r0, r.nb, 1.0, Xg + j * pstride + r0 * r.nb, r.nb, tmp + r0, 0.0, alpha + r0));
+    }
+    return gpx_lml(h, diag, r.n, 0, y, alpha, out3);   // ldl = 0: diag[i*0 + i]
+}
+
 int init_rank(MgRank& r, gpx_ctx* h, int P, int p, int64_t n, int nb, double* ws) {
     r.h = h; r.P = P; r.p = p; r.n = n; r.nb = nb; r.tpb = nb / GPX_T;
     const int64_t unit = (int64_t)nb * P;
@@ -333,20 +354,26 @@ extern "C" int gpx_mg_fit_grad(gpx_handle h, int kind, const double* X, int64_t 
         gpx_set_error("gpx_mg_fit_grad: leading minor of order %d is not positive definite", info);
         return info;
     }
-    gpx_phase_mark(h, GPX_PH_SOLVE);
-    GPX_TRY(solve_lml(r, y, alpha, out3));
     if (!with_grad) {
+        gpx_phase_mark(h, GPX_PH_SOLVE);
+        GPX_TRY(solve_lml(r, y, alpha, out3));
         gpx_phase_mark(h, GPX_PH_END);
         return 0;
     }
+    // diag(L) is needed for the log-determinant after the factor buffer is recycled for X
+    double* diagL = r.stage[0];
+    double* tmpv = r.stage[0] + r.npad;
+    GPX_TRY(gpx_copy_strided(h, r.npad, r.Lfull, r.npad + 1, diagL, 1));
     gpx_phase_mark(h, GPX_PH_TRTRI);
     GPX_TRY(trtri_local(r));
     if (P > 1) {
         const size_t cnt = (size_t)r.npad * r.wloc;
         GPX_NCCL(g_nccl.AllGather(r.Xall + (size_t)r.p * cnt, r.Xall, cnt, NCCL_F64, (ncclComm_p)h->nccl_comm, S));
     }
-    gpx_phase_mark(h, GPX_PH_LAUUM);
     GPX_TRY(reorder_X(r));
+    gpx_phase_mark(h, GPX_PH_SOLVE);
+    GPX_TRY(solve_lml_from_inverse(r, y, alpha, tmpv, diagL, out3));
+    gpx_phase_mark(h, GPX_PH_LAUUM);
     GPX_TRY(lauum_local(r));
     gpx_phase_mark(h, GPX_PH_GRAD);
     GPX_CUDA(cudaMemsetAsync(grad, 0, ntheta * sizeof(double), S));

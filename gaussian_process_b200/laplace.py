@@ -53,13 +53,19 @@ class BinaryLaplace:
         dinv = eng.potrf(B)
         return B, dinv
 
-    def _newton_step(self, f, g, w, sw, L, dinv):
-        """b = W f + g; a = b - W^1/2 B^-1 W^1/2 K b; f_new = K a  (GP_binary...:109-111)."""
+    def _newton_step(self, f, g, w, sw, L, dinv, Linv=None):
+        """b = W f + g; a = b - W^1/2 B^-1 W^1/2 K b; f_new = K a  (GP_binary...:109-111).
+        With ``Linv`` (explicit inv(L), as the reference forms at :108) B^-1 is applied as L_inv^T (L_inv .): two
+        HBM-bound GEMVs without the sequential dependency of a triangular solve."""
         eng, n, npad = self.eng, self.n, self.npad
         b = eng.vec_op(5, n, eng.zeros(npad), x=w, y=f, z=g)
         t = eng.gemv(self.K, b, eng.zeros(npad), m=n, n=n)
         eng.vec_op(2, n, t, x=sw, y=t)
-        eng.potrs_vec(L, dinv, t)
+        if Linv is not None:
+            u = eng.gemv(Linv, t, eng.zeros(npad), m=n, n=n)
+            t = eng.gemv(Linv, u, eng.zeros(npad), trans=True, m=n, n=n)
+        else:
+            eng.potrs_vec(L, dinv, t)
         a = eng.vec_op(3, n, eng.zeros(npad), x=b, y=sw, z=t)
         f_new = eng.gemv(self.K, a, eng.zeros(npad), m=n, n=n)
         d = eng.vec_op(6, n, eng.zeros(npad), x=f_new, y=f)
@@ -75,10 +81,13 @@ class BinaryLaplace:
         fp = self._pad_vec(f_prior)
         self.g, self.w, self.sw = self._terms(0, yd, fp)
         self.L, self.dinv = self._factor_B(self.sw)
+        Linv = self.L.clone()                      # the reference forms inv(L) explicitly (:108) and returns it
+        eng.trtri(Linv, self.dinv)
+        self._Linv_full = Linv
         f = eng.zeros(self.npad)
         self.errors = []
         for i in range(max_iter):
-            f, _, err = self._newton_step(f, self.g, self.w, self.sw, self.L, self.dinv)
+            f, _, err = self._newton_step(f, self.g, self.w, self.sw, self.L, self.dinv, Linv)
             self.errors.append(err)
             if on_iter is not None:
                 on_iter(i, err)
@@ -140,8 +149,10 @@ class BinaryLaplace:
     def L_inverse_host(self) -> np.ndarray:
         """Dense inv(L) on the host (the reference returns it, GP_binary...:108,133)."""
         eng = self.eng
-        Li = self.L.clone()
-        eng.trtri(Li, self.dinv)
+        Li = getattr(self, "_Linv_full", None)
+        if Li is None:
+            Li = self.L.clone()
+            eng.trtri(Li, self.dinv)
         return eng.to_host(Li[:self.n, :self.n])
 
 
