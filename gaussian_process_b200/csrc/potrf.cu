@@ -17,9 +17,8 @@ namespace {
 constexpr int LT = 128;          // leaf size
 constexpr int LB = 4;            // register block edge: thread (bi,bj) owns the 4x4 block of the lower triangle
 constexpr int NBK = LT / LB;     // 32 block rows -> 528 lower blocks
-constexpr int LLD = LT + 4;      // smem leading dimension (rows stay 16-byte aligned)
 constexpr int LEAF_THREADS = 544;
-constexpr int LEAF_SMEM = (LT * LLD + LT) * (int)sizeof(double);
+constexpr int LEAF_SMEM = (NBK * 578 + LT) * (int)sizeof(double);
 
 // One CTA factors one 128x128 diagonal block and inverts the factor.  The whole lower triangle lives in
 // REGISTERS (one 4x4 block per thread); shared memory only carries the finished panel values:
@@ -29,17 +28,22 @@ constexpr int LEAF_SMEM = (LT * LLD + LT) * (int)sizeof(double);
 // triangle of the same smem tile:  S(lower+diag) = L, S(strict upper) = X^T, dd = diag(X).
 //  A tile <- L (upper zeroed) ; Dinv tile <- L^-1 (upper zeroed)
 // info: first failing pivot (global 1-based index) is recorded once.
+// 4x4 blocks are stored block-major with 16-byte skews (block = 18 doubles, block row = 578 doubles) so that a warp whose
+// lanes read the same chunk of 32 different blocks -- along a block row or a block column -- hits distinct bank groups.
+__device__ __forceinline__ int soff(int a, int b) { return (a >> 2) * 578 + (b >> 2) * 18 + (a & 3) * 4 + (b & 3); }
+__device__ long long g_leaf_dbg[8];
 __global__ void __launch_bounds__(LEAF_THREADS, 1)
 potrf_leaf_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ Dinv, int* info, int global_off,
                   int64_t strideA, int64_t strideD) {
     extern __shared__ __align__(16) double sm[];
     __shared__ int fail_col;
     double* S = sm;
-    double* dd = sm + LT * LLD;
+    double* dd = sm + NBK * 578;
     A += (int64_t)blockIdx.x * strideA;
     Dinv += (int64_t)blockIdx.x * strideD;
     global_off += blockIdx.x * LT;
     const int tid = threadIdx.x;
+    const long long t_start = clock64();
     int bi = -1, bj = -1;
     if (tid < NBK * (NBK + 1) / 2) {
         bi = (int)((sqrtf(8.f * tid + 1.f) - 1.f) * 0.5f);
@@ -59,6 +63,7 @@ potrf_leaf_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ Dinv
     }
     if (tid == 0) fail_col = -1;
     __syncthreads();
+    const long long t_loaded = clock64();
 
     for (int p = 0; p < NBK; ++p) {
         if (active && bi == p && bj == p) {   // ---- 4x4 Cholesky + inverse of the diagonal block, in registers
@@ -70,8 +75,13 @@ potrf_leaf_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ Dinv
 #pragma unroll
                 for (int m = 0; m < c; ++m) d -= l[c][m] * l[c][m];
                 if (!(d > 0.0) && bad < 0) bad = c;
-                const double lc = sqrt(d);
-                const double rc = 1.0 / lc;
+                // 1/sqrt(d) by rsqrt + one Newton step (shorter dependent chain than sqrt followed by a division),
+                // then L_cc = d * r corrected to full precision with one more FMA pair
+                double rc = rsqrt(d);
+                rc = rc * (1.5 - 0.5 * d * rc * rc);
+                double lc = d * rc;
+                lc = lc + 0.5 * rc * fma(-lc, lc, d);     // Newton on sqrt: lc += (d - lc^2) / (2 lc)
+                rc = rc + rc * fma(-lc, rc, 1.0);         // Newton on the reciprocal: rc += rc (1 - lc rc)
                 l[c][c] = lc;
                 x[c][c] = rc;
 #pragma unroll
@@ -96,9 +106,9 @@ potrf_leaf_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ Dinv
             for (int r = 0; r < LB; ++r) {
                 dd[LB * p + r] = x[r][r];
 #pragma unroll
-                for (int c = 0; c <= r; ++c) S[(LB * p + r) * LLD + LB * p + c] = l[r][c];
+                for (int c = 0; c <= r; ++c) S[soff(LB * p + r, LB * p + c)] = l[r][c];
 #pragma unroll
-                for (int c = 0; c < r; ++c) S[(LB * p + c) * LLD + LB * p + r] = x[r][c];   // X_pp^T above the diagonal
+                for (int c = 0; c < r; ++c) S[soff(LB * p + c, LB * p + r)] = x[r][c];   // X_pp^T above the diagonal
             }
         }
         __syncthreads();
@@ -109,7 +119,7 @@ potrf_leaf_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ Dinv
             for (int r = 0; r < LB; ++r) {
                 x[r][r] = dd[LB * p + r];
 #pragma unroll
-                for (int c = 0; c < r; ++c) x[r][c] = S[(LB * p + c) * LLD + LB * p + r];
+                for (int c = 0; c < r; ++c) x[r][c] = S[soff(LB * p + c, LB * p + r)];
             }
 #pragma unroll
             for (int r = 0; r < LB; ++r) {
@@ -121,7 +131,7 @@ potrf_leaf_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ Dinv
                     for (int m = 0; m <= c; ++m) v += a[r][m] * x[c][m];
                     o[c] = v;
                 }
-                double2* dst = reinterpret_cast<double2*>(S + (LB * bi + r) * LLD + LB * p);
+                double2* dst = reinterpret_cast<double2*>(S + soff(LB * bi + r, LB * p));
                 dst[0] = make_double2(o[0], o[1]);
                 dst[1] = make_double2(o[2], o[3]);
             }
@@ -131,8 +141,8 @@ potrf_leaf_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ Dinv
             double li[LB][LB], lj[LB][LB];
 #pragma unroll
             for (int r = 0; r < LB; ++r) {
-                const double2* pi_ = reinterpret_cast<const double2*>(S + (LB * bi + r) * LLD + LB * p);
-                const double2* pj_ = reinterpret_cast<const double2*>(S + (LB * bj + r) * LLD + LB * p);
+                const double2* pi_ = reinterpret_cast<const double2*>(S + soff(LB * bi + r, LB * p));
+                const double2* pj_ = reinterpret_cast<const double2*>(S + soff(LB * bj + r, LB * p));
                 double2 u0 = pi_[0], u1 = pi_[1], w0 = pj_[0], w1 = pj_[1];
                 li[r][0] = u0.x; li[r][1] = u0.y; li[r][2] = u1.x; li[r][3] = u1.y;
                 lj[r][0] = w0.x; lj[r][1] = w0.y; lj[r][2] = w1.x; lj[r][3] = w1.y;
@@ -157,6 +167,7 @@ potrf_leaf_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ Dinv
         return;
     }
 
+    const long long t_fact = clock64();
     // ---- X = L^-1, right-looking over block rows k: acc_ij = sum_{k} L_ik X_kj ; X_ij = -X_ii acc_ij
     double acc[LB][LB];
 #pragma unroll
@@ -170,7 +181,7 @@ potrf_leaf_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ Dinv
             for (int r = 0; r < LB; ++r) {
                 x[r][r] = dd[LB * k + r];
 #pragma unroll
-                for (int c = 0; c < r; ++c) x[r][c] = S[(LB * k + c) * LLD + LB * k + r];
+                for (int c = 0; c < r; ++c) x[r][c] = S[soff(LB * k + c, LB * k + r)];
             }
 #pragma unroll
             for (int c = 0; c < LB; ++c) {
@@ -182,7 +193,7 @@ potrf_leaf_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ Dinv
                     for (int m = 0; m <= r; ++m) v += x[r][m] * acc[m][c];
                     o[r] = -v;
                 }
-                double2* dst = reinterpret_cast<double2*>(S + (LB * bj + c) * LLD + LB * k);
+                double2* dst = reinterpret_cast<double2*>(S + soff(LB * bj + c, LB * k));
                 dst[0] = make_double2(o[0], o[1]);
                 dst[1] = make_double2(o[2], o[3]);
             }
@@ -192,14 +203,14 @@ potrf_leaf_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ Dinv
             double li[LB][LB], xt[LB][LB];     // xt[c][m] = X_kj[m][c]
 #pragma unroll
             for (int r = 0; r < LB; ++r) {
-                const double2* pi_ = reinterpret_cast<const double2*>(S + (LB * bi + r) * LLD + LB * k);
+                const double2* pi_ = reinterpret_cast<const double2*>(S + soff(LB * bi + r, LB * k));
                 double2 u0 = pi_[0], u1 = pi_[1];
                 li[r][0] = u0.x; li[r][1] = u0.y; li[r][2] = u1.x; li[r][3] = u1.y;
             }
             if (bj < k) {
 #pragma unroll
                 for (int c = 0; c < LB; ++c) {
-                    const double2* px = reinterpret_cast<const double2*>(S + (LB * bj + c) * LLD + LB * k);
+                    const double2* px = reinterpret_cast<const double2*>(S + soff(LB * bj + c, LB * k));
                     double2 u0 = px[0], u1 = px[1];
                     xt[c][0] = u0.x; xt[c][1] = u0.y; xt[c][2] = u1.x; xt[c][3] = u1.y;
                 }
@@ -208,7 +219,7 @@ potrf_leaf_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ Dinv
                 for (int c = 0; c < LB; ++c)
 #pragma unroll
                     for (int m = 0; m < LB; ++m)
-                        xt[c][m] = (m == c) ? dd[LB * k + c] : (m > c ? S[(LB * k + c) * LLD + LB * k + m] : 0.0);
+                        xt[c][m] = (m == c) ? dd[LB * k + c] : (m > c ? S[soff(LB * k + c, LB * k + m)] : 0.0);
             }
 #pragma unroll
             for (int r = 0; r < LB; ++r)
@@ -219,10 +230,17 @@ potrf_leaf_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ Dinv
         }
     }
     __syncthreads();
+    const long long t_inv = clock64();
     for (int idx = tid; idx < LT * LT; idx += LEAF_THREADS) {
         int i = idx >> 7, j = idx & 127;
-        A[(int64_t)i * lda + j] = (j <= i) ? S[i * LLD + j] : 0.0;
-        Dinv[idx] = (j < i) ? S[j * LLD + i] : (j == i ? dd[i] : 0.0);
+        A[(int64_t)i * lda + j] = (j <= i) ? S[soff(i, j)] : 0.0;
+        Dinv[idx] = (j < i) ? S[soff(j, i)] : (j == i ? dd[i] : 0.0);
+    }
+    if (tid == 0 && blockIdx.x == 0) {
+        g_leaf_dbg[0] = t_loaded - t_start;
+        g_leaf_dbg[1] = t_fact - t_loaded;
+        g_leaf_dbg[2] = t_inv - t_fact;
+        g_leaf_dbg[3] = clock64() - t_inv;
     }
 }
 
@@ -501,4 +519,8 @@ int gpx_trsm_left_prefix_block(gpx_ctx* h, const double* L, int64_t n, int64_t l
                                int P, int p, int nb) {
     PrefixMap pm{P, p, nb};
     return trsm_left_prefix(h, L, n, ldl, dinv, B, ldb, 0, pm);
+}
+
+extern "C" int gpx_debug_leaf_cycles(long long* out4) {
+    return cudaMemcpyFromSymbol(out4, g_leaf_dbg, 4 * sizeof(long long)) == cudaSuccess ? 0 : GPX_E_CUDA;
 }
