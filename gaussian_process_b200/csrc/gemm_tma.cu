@@ -1,12 +1,14 @@
-// TMA-fed variant of the FP64 DMMA GEMM for the case both operands are k-major (the Cholesky trailing update
-// C -= A B^T and the TRSM update GEMMs): operand slabs are fetched by the Tensor Memory Accelerator
-// (cp.async.bulk.tensor.2d, SASS UTMALDG) into 128-byte-swizzled shared memory and handed to the DMMA warps through
-// an mbarrier full/empty ring -- no per-thread address arithmetic, no __syncthreads in the main loop.
+// TMA-fed FP64 DMMA GEMM (all four operand layouts; unbatched, out-of-place launches): operand slabs are fetched by the
+// Tensor Memory Accelerator (cp.async.bulk.tensor.2d, SASS UTMALDG) into 128-byte-swizzled shared memory and handed to the
+// DMMA warps through an mbarrier full/empty ring -- no per-thread address arithmetic, no __syncthreads in the main loop.
 //
-//   smem stage = A[128][16] + B[TN][16] doubles, dense, CU_TENSOR_MAP_SWIZZLE_128B (one row = 128 B = 8 chunks of 16 B,
-//   chunk index XOR (row & 7)).  Fragment loads stay bank-conflict free by permuting k inside a 16-slab:
-//   lane (g,t) at step j reads k = 8*(t>>1) + 2*j + (t&1)  ->  chunk' = (4*(t>>1) + j) ^ g,  so the 16 lanes of a half
-//   warp hit 16 distinct 8-byte bank pairs.  A and B use the same permutation, so the MMA still sums every k once.
+//   k-major operand   : one box {16 k, rows} -> smem [rows][16] doubles (row = 128 B = 8 chunks of 16 B, chunk ^= row & 7)
+//   k-strided operand : rows/16 boxes {16 m, 16 k} -> smem [box][16 k][16 m]            (chunk ^= k & 7)
+//   Both stay bank-conflict free for the 64-bit fragment loads of mma.m8n8k4 with
+//     k(t, j) = 8*(j>>1) + ({0,3,4,7}[t] ^ (j&1))        (a permutation of the 16 k of a slab, shared by A and B)
+//     k-major fragment rows permuted inside each group of 8:  rho(g) = [0,1,4,5,2,3,6,7][g]
+//   (16 lanes of a half warp then hit 16 distinct 8-byte bank pairs in either layout); the permutations only relabel
+//   which accumulator a lane owns, the epilogue undoes them (column pairs stay adjacent: rho(2t), rho(2t)+1).
 //   Producer = thread 0: refills the stage consumed two slabs ago (waits on its `empty` mbarrier), consumers wait on
 //   `full`, arrive on `empty`.  Two 4-warp CTAs per SM as in gemm.cu.
 #include <cuda.h>
@@ -75,7 +77,9 @@ __device__ __forceinline__ int mapped_pos(const GemmArgs& p, int col0) {
     return ((lb + p.cyc_q0) * p.cyc_P + p.cyc_p) * bw + col0 % bw - p.cyc_row_base;
 }
 
-template <int TN>
+__device__ __forceinline__ int rho8(int g) { return (g & 1) | (((g >> 1) & 1) << 2) | ((g >> 2) << 1); }
+
+template <bool A_KM, bool B_KM, int TN>
 __global__ void __launch_bounds__(TCfg<TN>::NT, 2)
 dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, GemmArgs p) {
     using C_ = TCfg<TN>;
@@ -123,8 +127,19 @@ dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         const unsigned fb = bar_full + s * 8;
         mbar_expect_tx(fb, C_::STAGE_BYTES);
         const unsigned dstA = base + s * C_::STAGE_BYTES;
-        tma_load_2d(dstA, &mapA, kbeg + slab * BK, row0, fb);
-        tma_load_2d(dstA + C_::A_BYTES, &mapB, kbeg + slab * BK, brow0, fb);
+        const int k0 = kbeg + slab * BK;
+        if (A_KM) {
+            tma_load_2d(dstA, &mapA, k0, row0, fb);
+        } else {
+#pragma unroll
+            for (int b = 0; b < BM / 16; ++b) tma_load_2d(dstA + b * 2048, &mapA, row0 + 16 * b, k0, fb);
+        }
+        if (B_KM) {
+            tma_load_2d(dstA + C_::A_BYTES, &mapB, k0, brow0, fb);
+        } else {
+#pragma unroll
+            for (int b = 0; b < TN / 16; ++b) tma_load_2d(dstA + C_::A_BYTES + b * 2048, &mapB, brow0 + 16 * b, k0, fb);
+        }
     };
     if (tid == 0) {
         const int npre = nk < STAGES ? nk : STAGES;
@@ -133,9 +148,12 @@ dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
 
     // per-lane constant parts of the swizzled fragment addresses (generic pointers for plain LDS)
     const uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
-    const int a_lane = (wm0 + g) * 128 + (t & 1) * 8;
-    const int b_lane = (wn0 + g) * 128 + (t & 1) * 8;
-    const int kch = (t >> 1) * 4;
+    const int rg = rho8(g);
+    const int s0t = (t == 0) ? 0 : (t == 1 ? 3 : (t == 2 ? 4 : 7));
+    // k-major: byte offset = (row)*128 + ((k>>1) ^ (row&7))*16 + (k&1)*8, row = w0 + 8i + rho(g)
+    // k-strided: byte offset = (m>>4)*2048 + k*128 + (((m&15)>>1) ^ (k&7))*16 + (m&1)*8, m = w0 + 8i + g
+    const int a_km_lane = (wm0 + rg) * 128, b_km_lane = (wn0 + rg) * 128;
+    const int a_ks_lane = (wm0 >> 4) * 2048 + (g & 1) * 8, b_ks_lane = (wn0 >> 4) * 2048 + (g & 1) * 8;
 
     for (int kt = 0; kt < nk; ++kt) {
         if (tid == 0 && kt >= 2) {           // refill the stage consumed two slabs ago
@@ -152,12 +170,19 @@ dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         const uint8_t* b_s = a_s + C_::A_BYTES;
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
-            const int sw = ((kch + j4) ^ g) << 4;   // swizzled 16-byte chunk
+            const int kap = 8 * (j4 >> 1) + (s0t ^ (j4 & 1));                       // this lane's k inside the slab
+            const int sw_km = (((kap >> 1) ^ rg) << 4) + (kap & 1) * 8;             // k-major: swizzled chunk + half
+            const int sw_ks0 = kap * 128 + ((((g >> 1)) ^ (kap & 7)) << 4);         // k-strided, even fragment (m&15 < 8)
+            const int sw_ks1 = kap * 128 + (((4 + (g >> 1)) ^ (kap & 7)) << 4);     // k-strided, odd fragment
             double af[8], bf[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) af[i] = *reinterpret_cast<const double*>(a_s + a_lane + i * 1024 + sw);
+            for (int i = 0; i < 8; ++i)
+                af[i] = A_KM ? *reinterpret_cast<const double*>(a_s + a_km_lane + i * 1024 + sw_km)
+                             : *reinterpret_cast<const double*>(a_s + a_ks_lane + (i >> 1) * 2048 + ((i & 1) ? sw_ks1 : sw_ks0));
 #pragma unroll
-            for (int j = 0; j < 4; ++j) bf[j] = *reinterpret_cast<const double*>(b_s + b_lane + j * 1024 + sw);
+            for (int j = 0; j < 4; ++j)
+                bf[j] = B_KM ? *reinterpret_cast<const double*>(b_s + b_km_lane + j * 1024 + sw_km)
+                             : *reinterpret_cast<const double*>(b_s + b_ks_lane + (j >> 1) * 2048 + ((j & 1) ? sw_ks1 : sw_ks0));
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -170,10 +195,10 @@ dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     const double alpha = p.alpha, beta = p.beta;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const int r = row0 + wm0 + i * 8 + g;
+        const int r = row0 + wm0 + i * 8 + (A_KM ? rg : g);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int c = col0 + wn0 + j * 8 + 2 * t;
+            const int c = col0 + wn0 + j * 8 + (B_KM ? rho8(2 * t) : 2 * t);
             double2* dst = reinterpret_cast<double2*>(C + (int64_t)r * p.ldc + c);
             double2 v;
             v.x = alpha * acc[i][j][0];
@@ -206,12 +231,28 @@ int tma_init() {
         return g_tma_state = -1;
     }
     g_encode = (EncodeTiledFn)fn;
-    if (cudaFuncSetAttribute(dgemm_dmma_tma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCfg<64>::SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(dgemm_dmma_tma_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess) {
+    bool ok = true;
+#define CFG(a, b)                                                                                                              \
+    ok = ok && cudaFuncSetAttribute(dgemm_dmma_tma_kernel<a, b, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCfg<64>::SMEM) == cudaSuccess && \
+         cudaFuncSetAttribute(dgemm_dmma_tma_kernel<a, b, 64>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) == cudaSuccess;
+    CFG(true, true) CFG(true, false) CFG(false, true) CFG(false, false)
+#undef CFG
+    if (!ok) {
         cudaGetLastError();
         return g_tma_state = -1;
     }
     return g_tma_state = 1;
+}
+
+// k-strided operand: K x cols doubles with leading dimension ld; box = 16 (cols) x 16 (k)
+int make_map_ks(CUtensorMap* m, const double* ptr, int64_t cols, int64_t K, int64_t ld) {
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)K};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
+    cuuint32_t box[2] = {16, (cuuint32_t)BK};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -1;
 }
 
 // k-major operand: rows x K doubles with leading dimension ld; box = 16 (k) x box_rows
@@ -229,16 +270,20 @@ int make_map(CUtensorMap* m, const double* ptr, int64_t rows, int64_t K, int64_t
 
 // Returns 1 if the launch was done through the TMA kernel, 0 if the caller must use the cp.async kernel, <0 on error.
 int gpx_gemm_tma_try_launch(gpx_ctx* h, const GemmArgs& a, double flops_exec) {
-    if (!(a.a_kmajor && a.b_kmajor) || a.batch > 1 || a.C == a.A || a.C == a.B) return 0;
+    if (a.batch > 1 || a.C == a.A || a.C == a.B) return 0;
     if ((a.lda % 2) || (a.ldb % 2)) return 0;
     if (tma_init() != 1) return 0;
     constexpr int TN = 64;
     alignas(64) CUtensorMap mapA, mapB;
     const int64_t rowsB = a.cyc_P > 0 && a.cyc_b_rows ? a.M : a.N;
-    if (make_map(&mapA, a.A, a.M, a.K, a.lda, BM) != 0 || make_map(&mapB, a.B, rowsB, a.K, a.ldb, TN) != 0) return 0;
+    if ((a.a_kmajor ? make_map(&mapA, a.A, a.M, a.K, a.lda, BM) : make_map_ks(&mapA, a.A, a.M, a.K, a.lda)) != 0) return 0;
+    if ((a.b_kmajor ? make_map(&mapB, a.B, rowsB, a.K, a.ldb, TN) : make_map_ks(&mapB, a.B, rowsB, a.K, a.ldb)) != 0) return 0;
     dim3 grid(a.N / TN, a.M / BM, 1);
     if (h->timing_on) gpx_timing_gemm_begin(h, flops_exec);
-    dgemm_dmma_tma_kernel<TN><<<grid, TCfg<TN>::NT, TCfg<TN>::SMEM, h->stream>>>(mapA, mapB, a);
+    if (a.a_kmajor && a.b_kmajor) dgemm_dmma_tma_kernel<true, true, TN><<<grid, TCfg<TN>::NT, TCfg<TN>::SMEM, h->stream>>>(mapA, mapB, a);
+    else if (a.a_kmajor) dgemm_dmma_tma_kernel<true, false, TN><<<grid, TCfg<TN>::NT, TCfg<TN>::SMEM, h->stream>>>(mapA, mapB, a);
+    else if (a.b_kmajor) dgemm_dmma_tma_kernel<false, true, TN><<<grid, TCfg<TN>::NT, TCfg<TN>::SMEM, h->stream>>>(mapA, mapB, a);
+    else dgemm_dmma_tma_kernel<false, false, TN><<<grid, TCfg<TN>::NT, TCfg<TN>::SMEM, h->stream>>>(mapA, mapB, a);
     GPX_CHECK_LAUNCH(h);
     gpx_timing_gemm_end(h);
     return 1;
