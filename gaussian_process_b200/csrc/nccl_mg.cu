@@ -136,38 +136,36 @@ int64_t first_local_block_after(const MgRank& r, int64_t j) {  // smallest q wit
     return (j - r.p) / r.P + 1;
 }
 
-// Xall[rank][npad][wloc] (rank-major, as all-gathered) -> Xg[block][npad][nb] in GLOBAL block order (panel-major);
-// only rows at/below each block's diagonal are copied (the rest of X is zero and never read).  Xg reuses Lfull.
+// Xall[rank][npad][wloc] (rank-major, as all-gathered) -> Xf[npad][npad] row-major in GLOBAL column order; only rows
+// at/below each block's diagonal are copied (the rest of X is zero and never read).  Xf reuses the Lfull buffer.
 int reorder_X(MgRank& r) {
     for (int64_t i = 0; i < r.nblk; ++i) {
         const int src = (int)(i % r.P);
         const int64_t q = i / r.P, r0 = i * r.nb;
         const double* from = r.Xall + (size_t)src * r.npad * r.wloc + r0 * r.wloc + q * r.nb;
-        double* to = r.Lfull + (size_t)i * r.npad * r.nb + r0 * r.nb;
-        GPX_CUDA(cudaMemcpy2DAsync(to, r.nb * sizeof(double), from, r.wloc * sizeof(double), r.nb * sizeof(double),
+        double* to = r.Lfull + r0 * r.npad + r0;
+        GPX_CUDA(cudaMemcpy2DAsync(to, r.npad * sizeof(double), from, r.wloc * sizeof(double), r.nb * sizeof(double),
                                    r.npad - r0, cudaMemcpyDeviceToDevice, r.h->stream));
     }
     return 0;
 }
 
-// local block columns of K^-1 = X^T X (rows >= column block): one batched triangular DMMA launch per owned column
-// block j, batch index z <-> row block i = j + z, all reading the panel-major replicated X (Xg = Lfull buffer).
+// local block columns of K^-1 = X^T X (tiles on/below the diagonal): ONE triangular TMA-fed DMMA launch for all owned
+// block columns -- C = Kloc[npad][wloc], A(m,k) = X[k][m], B(k,n) = X[k][gcol(n)] with the block-cyclic column map,
+// k >= row tile (X is lower triangular), tiles above the diagonal skipped; row tiles are scheduled longest-k first.
 int lauum_local(MgRank& r) {
-    const double* Xg = r.Lfull;
-    const int64_t pstride = r.npad * r.nb;   // elements per panel
-    for (int64_t q = 0; q < r.nloc; ++q) {
-        const int64_t j = q * r.P + r.p, kbase = j * r.nb;
-        GemmArgs a{};
-        a.alpha = 1.0; a.beta = 0.0;
-        a.batch = (int)(r.nblk - j);
-        a.A = Xg + j * pstride + kbase * r.nb; a.lda = r.nb; a.a_kmajor = 0; a.sA = pstride;
-        a.B = a.A; a.ldb = r.nb; a.b_kmajor = 0; a.sB = 0;
-        a.C = r.Kloc + kbase * r.wloc + q * r.nb; a.ldc = r.wloc; a.sC = (int64_t)r.nb * r.wloc;
-        a.M = r.nb; a.N = r.nb; a.K = (int)(r.npad - kbase);
-        a.kb_mode = 1; a.kb_batch = r.nb; a.kb_const = 0;
-        GPX_TRY(gpx_gemm_launch(r.h, a));
-    }
-    return 0;
+    const double* Xf = r.Lfull;
+    GemmArgs a{};
+    a.alpha = 1.0; a.beta = 0.0;
+    a.batch = 1;
+    a.A = Xf; a.lda = r.npad; a.a_kmajor = 0;
+    a.B = Xf; a.ldb = r.npad; a.b_kmajor = 0;
+    a.C = r.Kloc; a.ldc = r.wloc;
+    a.M = (int)r.npad; a.N = (int)r.wloc; a.K = (int)r.npad;
+    a.kb_mode = 1;
+    a.lower_only = 1;
+    a.cyc_P = r.P; a.cyc_p = r.p; a.cyc_tpb = r.tpb; a.cyc_q0 = 0; a.cyc_row_base = 0; a.cyc_b_rows = 1;
+    return gpx_gemm_launch(r.h, a);
 }
 
 __global__ void accumulate_kernel(int n, const double* __restrict__ x, double* __restrict__ acc) {
@@ -214,23 +212,22 @@ int solve_lml(MgRank& r, const double* y, double* alpha, double* out3) {
     return gpx_lml(h, r.Lfull, r.n, r.npad, y, alpha, out3);
 }
 
-// alpha = X^T (X y) from the replicated, panel-major inverse factor X = L^-1 (Xg in the Lfull buffer): two sweeps of
+// alpha = X^T (X y) from the replicated inverse factor X = L^-1 (row-major Xf in the Lfull buffer): two sweeps of
 // HBM-bound GEMVs with no sequential dependency (the reference's CO2 path forms alpha the same way, CO2...:144-145).
 // `diag` holds diag(L) saved before the factor buffer was recycled; out3 as gpx_lml.
 int solve_lml_from_inverse(MgRank& r, const double* y, double* alpha, double* tmp, const double* diag, double* out3) {
     gpx_ctx* h = r.h;
-    const double* Xg = r.Lfull;
-    const int64_t pstride = r.npad * r.nb;
+    const double* Xf = r.Lfull;
     GPX_CUDA(cudaMemsetAsync(tmp, 0, r.npad * sizeof(double), h->stream));
     GPX_CUDA(cudaMemsetAsync(alpha, 0, r.npad * sizeof(double), h->stream));
     GPX_CUDA(cudaMemcpyAsync(alpha, y, r.n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));   // padded y
     for (int64_t j = 0; j < r.nblk; ++j) {      // tmp = X y  (panel j contributes to rows >= j*nb)
         const int64_t r0 = j * r.nb;
-        GPX_TRY(gpx_gemv(h, 0, r.npad - r0, r.nb, 1.0, Xg + j * pstride + r0 * r.nb, r.nb, alpha + r0, 1.0, tmp + r0));
+        GPX_TRY(gpx_gemv(h, 0, r.npad - r0, r.nb, 1.0, Xf + r0 * r.npad + r0, r.npad, alpha + r0, 1.0, tmp + r0));
     }
     for (int64_t j = 0; j < r.nblk; ++j) {      // alpha_j = X_j^T tmp
         const int64_t r0 = j * r.nb;
-        GPX_TRY(gpx_gemv(h, 1, r.npad - r0, r.nb, 1.0, Xg + j * pstride + r0 * r.nb, r.nb, tmp + r0, 0.0, alpha + r0));
+        GPX_TRY(gpx_gemv(h, 1, r.npad - r0, r.nb, 1.0, Xf + r0 * r.npad + r0, r.npad, tmp + r0, 0.0, alpha + r0));
     }
     return gpx_lml(h, diag, r.n, 0, y, alpha, out3);   // ldl = 0: diag[i*0 + i]
 }
