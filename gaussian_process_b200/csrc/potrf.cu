@@ -10,6 +10,8 @@
 //   lauum  : out = Linv^T Linv (lower) in one triangular-aware launch.
 // Replaces np.linalg.cholesky / np.linalg.solve(L, .) / np.linalg.inv(L) / np.dot(inv(L.T), inv(L))
 // (SURVEY.md 8a rows A4, A5).
+#include <stdlib.h>
+#include <vector>
 #include "common.cuh"
 
 namespace {
@@ -65,94 +67,112 @@ potrf_leaf_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ Dinv
     __syncthreads();
     const long long t_loaded = clock64();
 
-    for (int p = 0; p < NBK; ++p) {
-        if (active && bi == p && bj == p) {   // ---- 4x4 Cholesky + inverse of the diagonal block, in registers
-            double l[LB][LB], x[LB][LB];
-            int bad = -1;
+    // ---- factorisation with intra-kernel look-ahead: in every step ALL trailing blocks apply the rank-4 update of
+    // panel p, and the owner of the next diagonal block factors it right away (its ~700-cycle serial chain overlaps
+    // the bulk update of the other threads); the panel multiply follows after one barrier.
+    auto diag_factor = [&](int p) {        // thread (p,p): 4x4 Cholesky + inverse of the diagonal block, in registers
+        double l[LB][LB], x[LB][LB];
+        int bad = -1;
 #pragma unroll
-            for (int c = 0; c < LB; ++c) {
-                double d = a[c][c];
+        for (int c = 0; c < LB; ++c) {
+            double d = a[c][c];
 #pragma unroll
-                for (int m = 0; m < c; ++m) d -= l[c][m] * l[c][m];
-                if (!(d > 0.0) && bad < 0) bad = c;
-                // 1/sqrt(d) by rsqrt + one Newton step (shorter dependent chain than sqrt followed by a division),
-                // then L_cc = d * r corrected to full precision with one more FMA pair
-                double rc = rsqrt(d);
-                rc = rc * (1.5 - 0.5 * d * rc * rc);
-                double lc = d * rc;
-                lc = lc + 0.5 * rc * fma(-lc, lc, d);     // Newton on sqrt: lc += (d - lc^2) / (2 lc)
-                rc = rc + rc * fma(-lc, rc, 1.0);         // Newton on the reciprocal: rc += rc (1 - lc rc)
-                l[c][c] = lc;
-                x[c][c] = rc;
+            for (int m = 0; m < c; ++m) d -= l[c][m] * l[c][m];
+            if (!(d > 0.0) && bad < 0) bad = c;
+            // 1/sqrt(d) by rsqrt + Newton (shorter dependent chain than sqrt followed by a division)
+            double rc = rsqrt(d);
+            rc = rc * (1.5 - 0.5 * d * rc * rc);
+            double lc = d * rc;
+            lc = lc + 0.5 * rc * fma(-lc, lc, d);
+            rc = rc + rc * fma(-lc, rc, 1.0);
+            l[c][c] = lc;
+            x[c][c] = rc;
 #pragma unroll
-                for (int r = c + 1; r < LB; ++r) {
-                    double v = a[r][c];
+            for (int r = c + 1; r < LB; ++r) {
+                double v = a[r][c];
 #pragma unroll
-                    for (int m = 0; m < c; ++m) v -= l[r][m] * l[c][m];
-                    l[r][c] = v * rc;
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < LB; ++c)
-#pragma unroll
-                for (int r = c + 1; r < LB; ++r) {
-                    double v = 0.0;
-#pragma unroll
-                    for (int m = c; m < r; ++m) v += l[r][m] * x[m][c];
-                    x[r][c] = -v * x[r][r];
-                }
-            if (bad >= 0) fail_col = LB * p + bad;
-#pragma unroll
-            for (int r = 0; r < LB; ++r) {
-                dd[LB * p + r] = x[r][r];
-#pragma unroll
-                for (int c = 0; c <= r; ++c) S[soff(LB * p + r, LB * p + c)] = l[r][c];
-#pragma unroll
-                for (int c = 0; c < r; ++c) S[soff(LB * p + c, LB * p + r)] = x[r][c];   // X_pp^T above the diagonal
+                for (int m = 0; m < c; ++m) v -= l[r][m] * l[c][m];
+                l[r][c] = v * rc;
             }
         }
-        __syncthreads();
-        if (fail_col >= 0) break;
-        if (active && bj == p && bi > p) {    // ---- panel: A_ip <- A_ip * L_pp^-T = A_ip * X_pp^T
-            double x[LB][LB];
 #pragma unroll
-            for (int r = 0; r < LB; ++r) {
-                x[r][r] = dd[LB * p + r];
+        for (int c = 0; c < LB; ++c)
 #pragma unroll
-                for (int c = 0; c < r; ++c) x[r][c] = S[soff(LB * p + c, LB * p + r)];
+            for (int r = c + 1; r < LB; ++r) {
+                double v = 0.0;
+#pragma unroll
+                for (int m = c; m < r; ++m) v += l[r][m] * x[m][c];
+                x[r][c] = -v * x[r][r];
             }
+        if (bad >= 0) fail_col = LB * p + bad;
 #pragma unroll
-            for (int r = 0; r < LB; ++r) {
-                double o[LB];
+        for (int r = 0; r < LB; ++r) {
+            dd[LB * p + r] = x[r][r];
 #pragma unroll
-                for (int c = 0; c < LB; ++c) {
-                    double v = 0.0;
+            for (int c = 0; c <= r; ++c) S[soff(LB * p + r, LB * p + c)] = l[r][c];
 #pragma unroll
-                    for (int m = 0; m <= c; ++m) v += a[r][m] * x[c][m];
-                    o[c] = v;
-                }
-                double2* dst = reinterpret_cast<double2*>(S + soff(LB * bi + r, LB * p));
-                dst[0] = make_double2(o[0], o[1]);
-                dst[1] = make_double2(o[2], o[3]);
-            }
+            for (int c = 0; c < r; ++c) S[soff(LB * p + c, LB * p + r)] = x[r][c];   // X_pp^T above the diagonal
         }
-        __syncthreads();
-        if (active && bj > p) {               // ---- rank-4 update of the trailing blocks (registers)
-            double li[LB][LB], lj[LB][LB];
+    };
+    auto panel_mul = [&](int p) {          // thread (i,p), i>p: A_ip <- A_ip * L_pp^-T = A_ip * X_pp^T
+        double x[LB][LB];
 #pragma unroll
-            for (int r = 0; r < LB; ++r) {
-                const double2* pi_ = reinterpret_cast<const double2*>(S + soff(LB * bi + r, LB * p));
-                const double2* pj_ = reinterpret_cast<const double2*>(S + soff(LB * bj + r, LB * p));
-                double2 u0 = pi_[0], u1 = pi_[1], w0 = pj_[0], w1 = pj_[1];
-                li[r][0] = u0.x; li[r][1] = u0.y; li[r][2] = u1.x; li[r][3] = u1.y;
-                lj[r][0] = w0.x; lj[r][1] = w0.y; lj[r][2] = w1.x; lj[r][3] = w1.y;
-            }
+        for (int r = 0; r < LB; ++r) {
+            x[r][r] = dd[LB * p + r];
+#pragma unroll
+            for (int c = 0; c < r; ++c) x[r][c] = S[soff(LB * p + c, LB * p + r)];
+        }
+        double o[LB][LB];
+#pragma unroll
+        for (int r = 0; r < LB; ++r)
+#pragma unroll
+            for (int c = 0; c < LB; ++c) o[r][c] = a[r][0] * x[c][0];
+#pragma unroll
+        for (int m = 1; m < LB; ++m)
 #pragma unroll
             for (int r = 0; r < LB; ++r)
 #pragma unroll
-                for (int c = 0; c < LB; ++c)
+                for (int c = m; c < LB; ++c) o[r][c] = fma(a[r][m], x[c][m], o[r][c]);
 #pragma unroll
-                    for (int m = 0; m < LB; ++m) a[r][c] -= li[r][m] * lj[c][m];
+        for (int r = 0; r < LB; ++r) {
+            double2* dst = reinterpret_cast<double2*>(S + soff(LB * bi + r, LB * p));
+            dst[0] = make_double2(o[r][0], o[r][1]);
+            dst[1] = make_double2(o[r][2], o[r][3]);
+        }
+    };
+    auto rank4_update = [&](int p) {       // thread (i,j), j>p: A_ij -= L_ip L_jp^T
+        double li[LB][LB], lj[LB][LB];
+#pragma unroll
+        for (int r = 0; r < LB; ++r) {
+            const double2* pi_ = reinterpret_cast<const double2*>(S + soff(LB * bi + r, LB * p));
+            const double2* pj_ = reinterpret_cast<const double2*>(S + soff(LB * bj + r, LB * p));
+            double2 u0 = pi_[0], u1 = pi_[1], w0 = pj_[0], w1 = pj_[1];
+            li[r][0] = u0.x; li[r][1] = u0.y; li[r][2] = u1.x; li[r][3] = u1.y;
+            lj[r][0] = w0.x; lj[r][1] = w0.y; lj[r][2] = w1.x; lj[r][3] = w1.y;
+        }
+        // m outermost: 16 independent FMAs between dependent ones (DFMA latency ~16 cycles would otherwise serialise)
+#pragma unroll
+        for (int m = 0; m < LB; ++m)
+#pragma unroll
+            for (int r = 0; r < LB; ++r)
+#pragma unroll
+                for (int c = 0; c < LB; ++c) a[r][c] = fma(-li[r][m], lj[c][m], a[r][c]);
+    };
+
+    if (active && bi == 0 && bj == 0) diag_factor(0);
+    __syncthreads();
+    if (fail_col < 0) {
+        if (active && bj == 0 && bi > 0) panel_mul(0);
+        __syncthreads();
+        for (int p = 0; p + 1 < NBK; ++p) {
+            if (active && bj > p) {
+                rank4_update(p);
+                if (bi == p + 1 && bj == p + 1) diag_factor(p + 1);
+            }
+            __syncthreads();
+            if (fail_col >= 0) break;
+            if (active && bj == p + 1 && bi > p + 1) panel_mul(p + 1);
+            __syncthreads();
         }
     }
     if (fail_col >= 0) {
@@ -168,38 +188,15 @@ potrf_leaf_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ Dinv
     }
 
     const long long t_fact = clock64();
-    // ---- X = L^-1, right-looking over block rows k: acc_ij = sum_{k} L_ik X_kj ; X_ij = -X_ii acc_ij
+    // ---- X = L^-1, right-looking over block rows k with look-ahead: acc_ij += L_ik X_kj for every i > k, and the
+    // threads of row k+1 finalise X_{k+1,j} = -X_{k+1,k+1} acc right away (one barrier per step).
     double acc[LB][LB];
 #pragma unroll
     for (int r = 0; r < LB; ++r)
 #pragma unroll
         for (int c = 0; c < LB; ++c) acc[r][c] = 0.0;
-    for (int k = 0; k < NBK; ++k) {
-        if (active && bi == k && bj < k) {    // finalise X_kj and publish it (transposed, above the diagonal)
-            double x[LB][LB];
-#pragma unroll
-            for (int r = 0; r < LB; ++r) {
-                x[r][r] = dd[LB * k + r];
-#pragma unroll
-                for (int c = 0; c < r; ++c) x[r][c] = S[soff(LB * k + c, LB * k + r)];
-            }
-#pragma unroll
-            for (int c = 0; c < LB; ++c) {
-                double o[LB];
-#pragma unroll
-                for (int r = 0; r < LB; ++r) {
-                    double v = 0.0;
-#pragma unroll
-                    for (int m = 0; m <= r; ++m) v += x[r][m] * acc[m][c];
-                    o[r] = -v;
-                }
-                double2* dst = reinterpret_cast<double2*>(S + soff(LB * bj + c, LB * k));
-                dst[0] = make_double2(o[0], o[1]);
-                dst[1] = make_double2(o[2], o[3]);
-            }
-        }
-        __syncthreads();
-        if (active && bi > k && bj <= k) {    // acc_ij += L_ik X_kj
+    for (int k = 0; k + 1 < NBK; ++k) {
+        if (active && bi > k && bj <= k) {
             double li[LB][LB], xt[LB][LB];     // xt[c][m] = X_kj[m][c]
 #pragma unroll
             for (int r = 0; r < LB; ++r) {
@@ -222,12 +219,37 @@ potrf_leaf_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ Dinv
                         xt[c][m] = (m == c) ? dd[LB * k + c] : (m > c ? S[soff(LB * k + c, LB * k + m)] : 0.0);
             }
 #pragma unroll
-            for (int r = 0; r < LB; ++r)
+            for (int m = 0; m < LB; ++m)
 #pragma unroll
-                for (int c = 0; c < LB; ++c)
+                for (int r = 0; r < LB; ++r)
 #pragma unroll
-                    for (int m = 0; m < LB; ++m) acc[r][c] += li[r][m] * xt[c][m];
+                    for (int c = 0; c < LB; ++c) acc[r][c] = fma(li[r][m], xt[c][m], acc[r][c]);
+            if (bi == k + 1) {                 // row k+1 is complete for every j <= k: finalise and publish (transposed)
+                const int kk = k + 1;
+                double x[LB][LB];
+#pragma unroll
+                for (int r = 0; r < LB; ++r) {
+                    x[r][r] = dd[LB * kk + r];
+#pragma unroll
+                    for (int c = 0; c < r; ++c) x[r][c] = S[soff(LB * kk + c, LB * kk + r)];
+                }
+#pragma unroll
+                for (int c = 0; c < LB; ++c) {
+                    double o[LB];
+#pragma unroll
+                    for (int r = 0; r < LB; ++r) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int m = 0; m <= r; ++m) v += x[r][m] * acc[m][c];
+                        o[r] = -v;
+                    }
+                    double2* dst = reinterpret_cast<double2*>(S + soff(LB * bj + c, LB * kk));
+                    dst[0] = make_double2(o[0], o[1]);
+                    dst[1] = make_double2(o[2], o[3]);
+                }
+            }
         }
+        __syncthreads();
     }
     __syncthreads();
     const long long t_inv = clock64();
@@ -306,8 +328,17 @@ int trsm_right_lt(gpx_ctx* h, double* B, int64_t m, int64_t ldb, const double* L
     return trsm_right_lt(h, B + h1, m, ldb, L + h1 * ldl + h1, h2, ldl, dinv + (h1 / LT) * LT * LT);
 }
 
+int potrf_la(gpx_ctx* h, double* A, int64_t n, int64_t lda, double* dinv, int goff, int nb);
+int la_threshold();
+int la_block(int64_t n);
+
 int potrf_rec(gpx_ctx* h, double* A, int64_t n, int64_t lda, double* dinv, int goff) {
     if (n == LT) return leaf(h, A, lda, dinv, goff);
+    // mid-size blocks: the serial chain of leaves / small GEMMs dominates -> look-ahead right-looking algorithm
+    if (n >= 1024 && n <= la_threshold()) {
+        const int nb = la_block(n);
+        if (n % nb == 0 && n >= 4 * nb) return potrf_la(h, A, n, lda, dinv, goff, nb);
+    }
     const int64_t h1 = half_tiles(n), h2 = n - h1;
     GPX_TRY(potrf_rec(h, A, h1, lda, dinv, goff));
     double* A21 = A + h1 * lda;
@@ -377,6 +408,107 @@ __global__ void copy_tiles_kernel(double* __restrict__ dst, int64_t ldd, int64_t
 
 }  // namespace
 
+
+namespace {
+// Right-looking blocked Cholesky with LOOK-AHEAD on two streams (used below a size threshold where the serial chain of
+// small kernels, not the DMMA pipe, bounds the recursive formulation).  Panel width nb; after panel j is final:
+//   chain stream H (high priority): a. update block column j+1 with panel j   b. factor panel j+1 (diag potrf + TRSM)
+//                                   c. [after the bulk update j-1 finished] update block column j+2 with panel j
+//   bulk stream S                 : update block columns >= j+3 with panel j
+// so the latency-bound panel chain runs concurrently with (and up to two panels ahead of) the DMMA-bound bulk updates.
+int potrf_la(gpx_ctx* h, double* A, int64_t n, int64_t lda, double* dinv, int goff, int nb) {
+    const int64_t nblk = n / nb;
+    const int tpb = nb / LT;
+    cudaStream_t S = h->stream, H = h->aux_stream;
+    std::vector<cudaEvent_t> evP(nblk), evS(nblk);
+    for (int64_t j = 0; j < nblk; ++j) {
+        GPX_CUDA(cudaEventCreateWithFlags(&evP[j], cudaEventDisableTiming));
+        GPX_CUDA(cudaEventCreateWithFlags(&evS[j], cudaEventDisableTiming));
+    }
+    cudaEvent_t ev0;
+    GPX_CUDA(cudaEventCreateWithFlags(&ev0, cudaEventDisableTiming));
+    GPX_CUDA(cudaEventRecord(ev0, S));            // everything queued on S so far (covariance build ...) precedes the chain
+    GPX_CUDA(cudaStreamWaitEvent(H, ev0, 0));
+    auto on_H = [&](auto&& fn) -> int { h->stream = H; int r = fn(); h->stream = S; return r; };
+    auto factor_panel = [&](int64_t j) -> int {
+        double* diag = A + j * nb * lda + j * nb;
+        double* dj = dinv + j * tpb * LT * LT;
+        GPX_TRY(potrf_rec(h, diag, nb, lda, dj, goff + (int)(j * nb)));
+        const int64_t below = n - (j + 1) * nb;
+        if (below > 0) GPX_TRY(trsm_right_lt(h, diag + (int64_t)nb * lda, below, lda, diag, nb, lda, dj));
+        return 0;
+    };
+    // update block columns [c0, c1) with panel j (rows from c0*nb down, lower tiles only)
+    auto update = [&](int64_t j, int64_t c0, int64_t c1) -> int {
+        if (c1 > nblk) c1 = nblk;
+        if (c0 >= c1) return 0;
+        const int64_t r0 = c0 * nb;
+        GemmArgs a = base_args();
+        a.A = A + r0 * lda + j * nb; a.lda = lda; a.a_kmajor = 1;
+        a.B = a.A; a.ldb = lda; a.b_kmajor = 1;
+        a.C = A + r0 * lda + r0; a.ldc = lda;
+        a.M = (int)(n - r0); a.N = (int)((c1 - c0) * nb); a.K = nb;
+        a.alpha = -1.0; a.beta = 1.0;
+        a.lower_only = 1;
+        return gpx_gemm_launch(h, a);
+    };
+    int rc = on_H([&]() { return factor_panel(0); });
+    if (rc == 0) rc = cudaEventRecord(evP[0], H) == cudaSuccess ? 0 : GPX_E_CUDA;
+    for (int64_t j = 0; j < nblk && rc == 0; ++j) {
+        // ---- chain (H)
+        if (j + 1 < nblk) {
+            rc = on_H([&]() {
+                GPX_TRY(update(j, j + 1, j + 2));
+                return factor_panel(j + 1);
+            });
+            if (rc == 0 && cudaEventRecord(evP[j + 1], H) != cudaSuccess) rc = GPX_E_CUDA;
+            if (rc == 0 && j + 2 < nblk) {
+                if (j >= 1) cudaStreamWaitEvent(H, evS[j - 1], 0);
+                rc = on_H([&]() { return update(j, j + 2, j + 3); });
+            }
+        }
+        // ---- bulk (S)
+        if (rc == 0) {
+            cudaStreamWaitEvent(S, evP[j], 0);
+            rc = update(j, j + 3, nblk);
+            if (rc == 0 && cudaEventRecord(evS[j], S) != cudaSuccess) rc = GPX_E_CUDA;
+        }
+    }
+    // join: S continues only after the chain has finished
+    if (rc == 0) {
+        cudaEventRecord(ev0, H);
+        cudaStreamWaitEvent(S, ev0, 0);
+    }
+    h->stream = S;
+    cudaStreamSynchronize(H);   // events are destroyed below; make sure H no longer references them
+    for (int64_t j = 0; j < nblk; ++j) {
+        cudaEventDestroy(evP[j]);
+        cudaEventDestroy(evS[j]);
+    }
+    cudaEventDestroy(ev0);
+    return rc;
+}
+
+int la_block(int64_t n) {   // panel width of the look-ahead algorithm
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("GPX_POTRF_LA_NB");
+        forced = e ? atoi(e) : 0;
+    }
+    if (forced > 0) return forced;
+    return n <= 8192 ? 128 : 256;
+}
+
+int la_threshold() {   // largest n factored by the look-ahead algorithm (0 disables it)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GPX_POTRF_LA_MAX");
+        v = e ? atoi(e) : 16384;
+    }
+    return v;
+}
+}  // namespace
+
 extern "C" int gpx_potrf(gpx_handle h, double* A, int64_t n, int64_t lda, double* dinv) {
     GPX_REQUIRE(h != nullptr, 1);
     GPX_REQUIRE(A != nullptr && ((uintptr_t)A % 16) == 0, 2);
@@ -443,10 +575,53 @@ int trtri_rec(gpx_ctx* h, double* A, int64_t n, int64_t lda, const double* dinv,
 }
 }  // namespace
 
+namespace {
+// Level-synchronous in-place inverse for a power-of-two tile count: the independent sub-problems of one recursion level
+// are ONE strided-batched GEMM launch (two launches per level, 2 log2(n/128) launches in all) while they are small; from
+// BIG_BLOCK on, each sub-problem is large enough for its own (TMA-fed) launch.
+int trtri_levels(gpx_ctx* h, double* A, int64_t n, int64_t lda, const double* dinv, double* work) {
+    const int nt = (int)(n / LT);
+    copy_tiles_kernel<<<nt, 256, 0, h->stream>>>(A, lda, (int64_t)LT * (lda + 1), dinv, (int64_t)LT * LT);
+    GPX_CHECK_LAUNCH(h);
+    constexpr int64_t BIG_BLOCK = 4096;
+    for (int64_t hs = LT; hs < n; hs *= 2) {
+        const int nsub = (int)(n / (2 * hs));
+        const int64_t sub_stride = 2 * hs * (lda + 1);
+        const int groups = hs >= BIG_BLOCK ? nsub : 1;          // separate launches for big sub-problems
+        const int per = hs >= BIG_BLOCK ? 1 : nsub;
+        for (int gi = 0; gi < groups; ++gi) {
+            double* base = A + (int64_t)gi * sub_stride;
+            double* wbase = work + (int64_t)gi * hs * hs;
+            GemmArgs a = base_args();  // T = A21 * A11inv  (k >= column tile)
+            a.A = base + hs * lda; a.lda = lda; a.a_kmajor = 1; a.sA = sub_stride;
+            a.B = base; a.ldb = lda; a.b_kmajor = 0; a.sB = sub_stride;
+            a.C = wbase; a.ldc = hs; a.sC = hs * hs;
+            a.M = (int)hs; a.N = (int)hs; a.K = (int)hs;
+            a.batch = per;
+            a.kb_mode = 2;
+            GPX_TRY(gpx_gemm_launch(h, a));
+            GemmArgs b = base_args();  // A21 = -A22inv * T  (k <= row tile)
+            b.A = base + hs * lda + hs; b.lda = lda; b.a_kmajor = 1; b.sA = sub_stride;
+            b.B = wbase; b.ldb = hs; b.b_kmajor = 0; b.sB = hs * hs;
+            b.C = base + hs * lda; b.ldc = lda; b.sC = sub_stride;
+            b.M = (int)hs; b.N = (int)hs; b.K = (int)hs;
+            b.batch = per;
+            b.alpha = -1.0;
+            b.ke_mode = 1;
+            b.rev_rows = 1;
+            GPX_TRY(gpx_gemm_launch(h, b));
+        }
+    }
+    return 0;
+}
+}  // namespace
+
 extern "C" int gpx_trtri(gpx_handle h, double* L, int64_t n, int64_t ldl, const double* dinv, double* work) {
     GPX_REQUIRE(h != nullptr, 1);
     GPX_REQUIRE(n > 0 && n % LT == 0, 3);
     GPX_REQUIRE(n == LT || work != nullptr, 6);
+    const int64_t nt = n / LT;
+    if (nt > 1 && (nt & (nt - 1)) == 0) return trtri_levels(h, L, n, ldl, dinv, work);
     return trtri_rec(h, L, n, ldl, dinv, work);
 }
 
