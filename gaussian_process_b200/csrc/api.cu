@@ -44,6 +44,7 @@ extern "C" int gpx_create(int device, gpx_handle* out) {
         int lo = 0, hi = 0;
         GPX_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         GPX_CUDA(cudaStreamCreateWithPriority(&h->aux_stream, cudaStreamNonBlocking, hi));
+        GPX_CUDA(cudaStreamCreateWithPriority(&h->aux2_stream, cudaStreamNonBlocking, hi));
     }
     GPX_CUDA(cudaEventCreateWithFlags(&h->ev_a, cudaEventDisableTiming));
     GPX_CUDA(cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming));
@@ -61,6 +62,7 @@ extern "C" int gpx_destroy(gpx_handle h) {
     if (h->d_partial) cudaFree(h->d_partial);
     if (h->d_theta) cudaFree(h->d_theta);
     if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+    if (h->aux2_stream) cudaStreamDestroy(h->aux2_stream);
     if (h->ev_a) cudaEventDestroy(h->ev_a);
     if (h->ev_b) cudaEventDestroy(h->ev_b);
     delete h;

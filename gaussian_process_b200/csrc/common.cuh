@@ -20,7 +20,7 @@ struct gpx_ctx {
     double* d_theta;     // 16 doubles of hyper-parameters for kernels
     // NCCL (optional, dlopen'ed)
     void* nccl_comm; int rank, world;
-    cudaStream_t aux_stream; cudaEvent_t ev_a, ev_b;
+    cudaStream_t aux_stream, aux2_stream; cudaEvent_t ev_a, ev_b;
     // optional instrumentation (timing.cu)
     int timing_on; void* timing;
 };

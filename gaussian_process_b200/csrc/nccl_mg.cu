@@ -294,46 +294,68 @@ extern "C" int gpx_mg_fit_grad(gpx_handle h, int kind, const double* X, int64_t 
     GPX_REQUIRE(P == 1 || h->nccl_comm != nullptr, 1);
     MgRank r;
     init_rank(r, h, P, p, n, nb, ws);
-    cudaStream_t S = h->stream, Cs = h->aux_stream;
-    cudaEvent_t ev_panel[2], ev_recv[2], ev_start;
-    for (int i = 0; i < 2; ++i) {
-        GPX_CUDA(cudaEventCreateWithFlags(&ev_panel[i], cudaEventDisableTiming));
-        GPX_CUDA(cudaEventCreateWithFlags(&ev_recv[i], cudaEventDisableTiming));
+    // Three streams: S = bulk trailing updates, H = panel chain (high priority), Cs = NCCL broadcasts + unpack.
+    //   after panel j is received:  H: owner(j+1): update column j+1, factor + pack panel j+1   (-> Cs broadcasts it)
+    //                                  owner(j+2): [after bulk update j-1] update column j+2
+    //                               S: update the local block columns with global index >= j+3
+    // so the latency-bound chain runs concurrently with, and up to two panels ahead of, the DMMA-bound bulk updates.
+    cudaStream_t S = h->stream, Cs = h->aux_stream, H = h->aux2_stream;
+    std::vector<cudaEvent_t> evPanel(r.nblk), evRecv(r.nblk), evS(r.nblk);
+    for (int64_t j = 0; j < r.nblk; ++j) {
+        GPX_CUDA(cudaEventCreateWithFlags(&evPanel[j], cudaEventDisableTiming));
+        GPX_CUDA(cudaEventCreateWithFlags(&evRecv[j], cudaEventDisableTiming));
+        GPX_CUDA(cudaEventCreateWithFlags(&evS[j], cudaEventDisableTiming));
     }
+    cudaEvent_t ev_start;
     GPX_CUDA(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
     GPX_CUDA(cudaMemsetAsync(h->d_info, 0, sizeof(int), S));
     GPX_CUDA(cudaMemsetAsync(r.Lfull, 0, (size_t)r.npad * r.npad * sizeof(double), S));
     gpx_phase_mark(h, GPX_PH_COV);
     GPX_TRY(cov_local(r, kind, X, D, theta_host, ntheta, s));
     gpx_phase_mark(h, GPX_PH_POTRF);
-    // ---- right-looking block-cyclic Cholesky with look-ahead
-    if (r.p == 0) GPX_TRY(panel_factor_pack(r, 0, r.stage[0]));
-    GPX_CUDA(cudaEventRecord(ev_panel[0], S));
     GPX_CUDA(cudaEventRecord(ev_start, S));
-    GPX_CUDA(cudaStreamWaitEvent(Cs, ev_start, 0));   // Lfull memset etc. precede any unpack
+    GPX_CUDA(cudaStreamWaitEvent(Cs, ev_start, 0));   // Lfull memset / covariance build precede the chain
+    GPX_CUDA(cudaStreamWaitEvent(H, ev_start, 0));
+    auto on_H = [&](auto&& fn) -> int { h->stream = H; int rc_ = fn(); h->stream = S; return rc_; };
+    if (r.p == 0) {
+        GPX_TRY(on_H([&]() { return panel_factor_pack(r, 0, r.stage[0]); }));
+        GPX_CUDA(cudaEventRecord(evPanel[0], H));
+    }
     for (int64_t j = 0; j < r.nblk; ++j) {
         const int sb = (int)(j & 1);
         const int owner = (int)(j % P);
         const int64_t rows = r.npad - j * r.nb;
         const size_t count = (size_t)rows * r.nb + (size_t)r.tpb * GPX_T * GPX_T;
-        GPX_CUDA(cudaStreamWaitEvent(Cs, ev_panel[sb], 0));
+        // ---- communication stream
+        if (owner == r.p) GPX_CUDA(cudaStreamWaitEvent(Cs, evPanel[j], 0));
+        if (j >= 2) GPX_CUDA(cudaStreamWaitEvent(Cs, evRecv[j - 2], 0));   // stage[sb] free (trivially true on Cs itself)
         if (P > 1) GPX_NCCL(g_nccl.Broadcast(r.stage[sb], r.stage[sb], count, NCCL_F64, owner, (ncclComm_p)h->nccl_comm, Cs));
         GPX_TRY(panel_unpack(r, j, r.stage[sb], Cs));
-        GPX_CUDA(cudaEventRecord(ev_recv[sb], Cs));
-        GPX_CUDA(cudaStreamWaitEvent(S, ev_recv[sb], 0));
-        const int64_t q_first = first_local_block_after(r, j);
+        GPX_CUDA(cudaEventRecord(evRecv[j], Cs));
+        // ---- chain stream
+        GPX_CUDA(cudaStreamWaitEvent(H, evRecv[j], 0));
         if (j + 1 < r.nblk && (int)((j + 1) % P) == r.p) {
-            const int64_t qn = (j + 1) / P;               // local index of the next panel (== q_first)
-            GPX_TRY(trailing_update(r, j, qn, qn + 1));
-            GPX_TRY(panel_factor_pack(r, j + 1, r.stage[sb ^ 1]));
-            GPX_CUDA(cudaEventRecord(ev_panel[sb ^ 1], S));
-            GPX_TRY(trailing_update(r, j, qn + 1, r.nloc));
-        } else {
-            if (j + 1 < r.nblk) GPX_CUDA(cudaEventRecord(ev_panel[sb ^ 1], S));  // keeps the event "fresh" on non-owners
-            GPX_TRY(trailing_update(r, j, q_first, r.nloc));
+            const int64_t q1 = (j + 1) / P;
+            GPX_TRY(on_H([&]() {
+                GPX_TRY(trailing_update(r, j, q1, q1 + 1));
+                return panel_factor_pack(r, j + 1, r.stage[sb ^ 1]);
+            }));
+            GPX_CUDA(cudaEventRecord(evPanel[j + 1], H));
         }
+        if (j + 2 < r.nblk && (int)((j + 2) % P) == r.p) {
+            const int64_t q2 = (j + 2) / P;
+            if (j >= 1) GPX_CUDA(cudaStreamWaitEvent(H, evS[j - 1], 0));
+            GPX_TRY(on_H([&]() { return trailing_update(r, j, q2, q2 + 1); }));
+        }
+        // ---- bulk stream
+        GPX_CUDA(cudaStreamWaitEvent(S, evRecv[j], 0));
+        GPX_TRY(trailing_update(r, j, first_local_block_after(r, j + 2), r.nloc));
+        GPX_CUDA(cudaEventRecord(evS[j], S));
     }
+    GPX_CUDA(cudaEventRecord(ev_start, H));
+    GPX_CUDA(cudaStreamWaitEvent(S, ev_start, 0));
     GPX_CUDA(cudaStreamSynchronize(Cs));
+    GPX_CUDA(cudaStreamSynchronize(H));
     int info = 0;
     GPX_TRY(gpx_read_info(h, &info));
     if (P > 1) {
@@ -342,9 +364,10 @@ extern "C" int gpx_mg_fit_grad(gpx_handle h, int kind, const double* X, int64_t 
         GPX_NCCL(g_nccl.AllReduce(h->d_info, h->d_info, 1, NCCL_I32, NCCL_MAX, (ncclComm_p)h->nccl_comm, S));
         GPX_TRY(gpx_read_info(h, &info));
     }
-    for (int i = 0; i < 2; ++i) {
-        cudaEventDestroy(ev_panel[i]);
-        cudaEventDestroy(ev_recv[i]);
+    for (int64_t j = 0; j < r.nblk; ++j) {
+        cudaEventDestroy(evPanel[j]);
+        cudaEventDestroy(evRecv[j]);
+        cudaEventDestroy(evS[j]);
     }
     cudaEventDestroy(ev_start);
     if (info > 0) {
