@@ -190,66 +190,69 @@ extern "C" int gpx_host_lml(gpx_handle h, int kind, const double* X, int64_t n, 
 // FP64 peak micro-benchmarks (register-resident issue loops)
 // ---------------------------------------------------------------------------------------------
 namespace {
-__global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* out) {
-    double c[16][2];
+// One 1024-thread block per SM (32 warps, 8 per scheduler), 8 independent accumulator chains per warp: exactly one
+// wave on any SM count, so the result cannot depend on how the block scheduler packs several blocks per SM.
+constexpr int PEAK_CHAINS = 8;
+__global__ void __launch_bounds__(1024, 1) dmma_peak_kernel(int iters, double* out) {
+    double c[PEAK_CHAINS][2];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) c[i][0] = c[i][1] = 0.0;
+    for (int i = 0; i < PEAK_CHAINS; ++i) c[i][0] = c[i][1] = 0.0;
     double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
+        for (int i = 0; i < PEAK_CHAINS; ++i)
             asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                          : "+d"(c[i][0]), "+d"(c[i][1])
                          : "d"(a), "d"(b));
     }
     double s = 0.0;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) s += c[i][0] + c[i][1];
+    for (int i = 0; i < PEAK_CHAINS; ++i) s += c[i][0] + c[i][1];
     if (s == 12345.678) out[0] = s;
 }
-__global__ void __launch_bounds__(256) dfma_peak_kernel(int iters, double* out) {
-    double c[16];
+__global__ void __launch_bounds__(1024, 1) dfma_peak_kernel(int iters, double* out) {
+    double c[PEAK_CHAINS];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) c[i] = threadIdx.x * 1e-3 + i;
+    for (int i = 0; i < PEAK_CHAINS; ++i) c[i] = threadIdx.x * 1e-3 + i;
     double a = 1.0 + threadIdx.x * 1e-9, b = 1e-9;
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) c[i] = fma(c[i], a, b);
+        for (int i = 0; i < PEAK_CHAINS; ++i) c[i] = fma(c[i], a, b);
     }
     double s = 0.0;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) s += c[i];
+    for (int i = 0; i < PEAK_CHAINS; ++i) s += c[i];
     if (s == 12345.678) out[0] = s;
 }
 // mixed: even warps issue DMMA, odd warps issue DFMA (8x the iterations: one DFMA warp-instruction is
-// 2 issue cycles, one DMMA 16) -- tells whether the two FP64 pipes run concurrently.
-__global__ void __launch_bounds__(256) mixed_peak_kernel(int iters, double* out) {
+// 2 issue cycles, one DMMA 16) -- tells whether the two FP64 pipes run concurrently (they do not: 35.5 TF).
+__global__ void __launch_bounds__(1024, 1) mixed_peak_kernel(int iters, double* out) {
     const int warp = threadIdx.x >> 5;
     double s = 0.0;
     double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
     if (warp & 1) {
-        double c[16];
+        double c[PEAK_CHAINS];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) c[i] = threadIdx.x * 1e-3 + i;
+        for (int i = 0; i < PEAK_CHAINS; ++i) c[i] = threadIdx.x * 1e-3 + i;
         for (int it = 0; it < iters * 8; ++it) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) c[i] = fma(c[i], a, 1e-9);
+            for (int i = 0; i < PEAK_CHAINS; ++i) c[i] = fma(c[i], a, 1e-9);
         }
 #pragma unroll
-        for (int i = 0; i < 16; ++i) s += c[i];
+        for (int i = 0; i < PEAK_CHAINS; ++i) s += c[i];
     } else {
-        double c[16][2];
+        double c[PEAK_CHAINS][2];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) c[i][0] = c[i][1] = 0.0;
+        for (int i = 0; i < PEAK_CHAINS; ++i) c[i][0] = c[i][1] = 0.0;
         for (int it = 0; it < iters; ++it) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
+            for (int i = 0; i < PEAK_CHAINS; ++i)
                 asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                              : "+d"(c[i][0]), "+d"(c[i][1])
                              : "d"(a), "d"(b));
         }
 #pragma unroll
-        for (int i = 0; i < 16; ++i) s += c[i][0] + c[i][1];
+        for (int i = 0; i < PEAK_CHAINS; ++i) s += c[i][0] + c[i][1];
     }
     if (s == 12345.678) out[0] = s;
 }
@@ -260,7 +263,9 @@ extern "C" int gpx_bench_fp64_peak(gpx_handle h, int use_dmma, int iters, double
     cudaEvent_t e0, e1;
     GPX_CUDA(cudaEventCreate(&e0));
     GPX_CUDA(cudaEventCreate(&e1));
-    const int blocks = 148 * 4, threads = 256;
+    cudaDeviceProp prop;
+    GPX_CUDA(cudaGetDeviceProperties(&prop, h->device));
+    const int blocks = prop.multiProcessorCount, threads = 1024;
     double best = 1e30;
     // An idle GPU needs up to ~1 s of load to reach its boost clocks: repeat until the best time stops improving.
     int stale = 0;
@@ -282,8 +287,9 @@ extern "C" int gpx_bench_fp64_peak(gpx_handle h, int use_dmma, int iters, double
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     const double warps = (double)blocks * threads / 32.0;
-    double flops = use_dmma ? warps * iters * 16.0 * 512.0 : warps * iters * 16.0 * 64.0;
-    if (use_dmma == 2) flops = 0.5 * warps * iters * 16.0 * 512.0 + 0.5 * warps * iters * 8.0 * 16.0 * 64.0;
+    const double ch = PEAK_CHAINS;
+    double flops = use_dmma ? warps * iters * ch * 512.0 : warps * iters * ch * 64.0;
+    if (use_dmma == 2) flops = 0.5 * warps * iters * ch * 512.0 + 0.5 * warps * iters * 8.0 * ch * 64.0;
     *ms_out = best;
     *tflops_out = flops / (best * 1e-3) / 1e12;
     return 0;
