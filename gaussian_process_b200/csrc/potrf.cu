@@ -480,7 +480,7 @@ int potrf_la(gpx_ctx* h, double* A, int64_t n, int64_t lda, double* dinv, int go
         cudaStreamWaitEvent(S, ev0, 0);
     }
     h->stream = S;
-    cudaStreamSynchronize(H);   // events are destroyed below; make sure H no longer references them
+    // no host synchronisation: destroying an event that is still pending only defers the release of its resources
     for (int64_t j = 0; j < nblk; ++j) {
         cudaEventDestroy(evP[j]);
         cudaEventDestroy(evS[j]);
@@ -509,23 +509,40 @@ int la_threshold() {   // largest n factored by the look-ahead algorithm (0 disa
 }
 }  // namespace
 
-extern "C" int gpx_potrf(gpx_handle h, double* A, int64_t n, int64_t lda, double* dinv) {
+extern "C" int gpx_potrf_async(gpx_handle h, double* A, int64_t n, int64_t lda, double* dinv) {
     GPX_REQUIRE(h != nullptr, 1);
     GPX_REQUIRE(A != nullptr && ((uintptr_t)A % 16) == 0, 2);
     GPX_REQUIRE(n > 0 && n % LT == 0, 3);
     GPX_REQUIRE(lda >= n && lda % 2 == 0, 4);
     GPX_REQUIRE(dinv != nullptr, 5);
-    GPX_CUDA(cudaMemsetAsync(h->d_info, 0, sizeof(int), h->stream));
     GPX_TRY(potrf_rec(h, A, n, lda, dinv, 0));
     const int nt = (int)(n / LT);
     if (nt > 1) {
         zero_upper_tiles_kernel<<<dim3(nt, nt), 256, 0, h->stream>>>(A, lda, nt);
         GPX_CHECK_LAUNCH(h);
     }
+    return 0;
+}
+
+extern "C" int gpx_potrf(gpx_handle h, double* A, int64_t n, int64_t lda, double* dinv) {
+    GPX_REQUIRE(h != nullptr, 1);
+    GPX_CUDA(cudaMemsetAsync(h->d_info, 0, sizeof(int), h->stream));
+    int r = gpx_potrf_async(h, A, n, lda, dinv);
+    if (r != 0) return r;
     int info = 0;
     GPX_TRY(gpx_read_info(h, &info));
     if (info > 0) gpx_set_error("gpx_potrf: leading minor of order %d is not positive definite", info);
     return info;
+}
+
+extern "C" int gpx_potrf_info(gpx_handle h, int* info_out) {
+    GPX_REQUIRE(h != nullptr && info_out != nullptr, 1);
+    int info = 0;
+    GPX_TRY(gpx_read_info(h, &info));
+    GPX_CUDA(cudaMemsetAsync(h->d_info, 0, sizeof(int), h->stream));   // read-and-clear: the flag is sticky across async calls
+    *info_out = info;
+    if (info > 0) gpx_set_error("gpx_potrf: leading minor of order %d is not positive definite", info);
+    return 0;
 }
 
 extern "C" int gpx_trsm(gpx_handle h, const double* L, int64_t n, int64_t ldl, const double* dinv, int trans,

@@ -137,6 +137,21 @@ class Engine:
         check(self.lib.gpx_potrf(self.h, self._p(A), n, A.stride(0), self._p(dinv)), "gpx_potrf")
         return dinv
 
+    def potrf_async(self, A):
+        """Like potrf() but returns after enqueueing (no host synchronisation); call potrf_check() later."""
+        self._sync_stream()
+        n = A.shape[0]
+        dinv = self.empty(n // GPX_TILE, GPX_TILE, GPX_TILE)
+        check(self.lib.gpx_potrf_async(self.h, self._p(A), n, A.stride(0), self._p(dinv)), "gpx_potrf_async")
+        return dinv
+
+    def potrf_check(self):
+        """Synchronise this handle's stream and raise LinAlgError if any async factorisation since the last check failed."""
+        self._sync_stream()
+        info = ctypes.c_int(0)
+        check(self.lib.gpx_potrf_info(self.h, ctypes.byref(info)), "gpx_potrf_info")
+        check(info.value, "gpx_potrf_async")
+
     def trsv(self, L, dinv, x, trans: bool = False):
         self._sync_stream()
         check(self.lib.gpx_trsv(self.h, self._p(L), L.shape[0], L.stride(0), self._p(dinv), int(trans), self._p(x)), "gpx_trsv")
@@ -366,6 +381,12 @@ class Engine:
 
 
 _engines = {}
+
+
+def new_engine(device: int = 0) -> Engine:
+    """A fresh handle on the same device (own scratch and helper streams): independent problems issued through different
+    engines, each under its own ``torch.cuda.stream``, run concurrently."""
+    return Engine(device)
 
 
 def get_engine(device: int = 0) -> Engine:

@@ -224,12 +224,29 @@ class MultiLaplaceNewton:
     across ranks: ``classes`` lists the classes this process owns; sums over classes are completed by
     ``allreduce`` (a callable on device tensors) when given."""
 
-    def __init__(self, eng: Engine, Ksub, C: int, n: int, classes: Optional[List[int]] = None, allreduce=None):
+    def __init__(self, eng: Engine, Ksub, C: int, n: int, classes: Optional[List[int]] = None, allreduce=None,
+                 concurrency: int = 4):
         self.eng, self.K, self.C, self.n, self.npad = eng, Ksub, int(C), int(n), Ksub.shape[0]
         self.classes = list(range(C)) if classes is None else list(classes)
         self.allreduce = allreduce
         self.errors: List[float] = []
         self.f = self.pi = None
+        # the per-class factorisations are independent: issue them through `concurrency` handles / CUDA streams so the
+        # latency-bound parts of one class overlap with the DMMA-bound parts of another
+        self.nstreams = max(1, min(int(concurrency), len(self.classes)))
+        self._lanes = None
+
+    def _make_lanes(self):
+        from .engine import new_engine
+        eng, npad = self.eng, self.npad
+        T = eng.torch
+        lanes = []
+        for k in range(self.nstreams):
+            st = T.cuda.Stream(device=eng.device)
+            with T.cuda.stream(st):
+                e = eng if self.nstreams == 1 else new_engine(eng.device.index)
+                lanes.append(dict(eng=e, stream=st, Ec=e.empty(npad, npad), work=e.empty(npad, npad), Esum=e.empty(npad, npad)))
+        return lanes
 
     def fit(self, y, tolerance: float = 1e-8, max_iter: int = 100, on_iter=None):
         eng, C, n, npad = self.eng, self.C, self.n, self.npad
@@ -241,26 +258,47 @@ class MultiLaplaceNewton:
         pi = eng.zeros(C, n)
         Linv = {c: eng.empty(npad, npad) for c in self.classes}
         sd = {c: eng.zeros(npad) for c in self.classes}
-        Esum = eng.empty(npad, npad)
-        Ec = eng.empty(npad, npad)
-        work = eng.empty(npad, npad)
+        if self._lanes is None:
+            self._lanes = self._make_lanes()
+        lanes = self._lanes
+        Esum = lanes[0]["Esum"]
+        main = T.cuda.current_stream(eng.device)
         self.errors = []
         for it in range(max_iter):
             eng._sync_stream()
             _chk(eng, lib.gpx_softmax_classes(eng.h, C, n, n, eng._p(f), eng._p(pi)), "gpx_softmax_classes")
-            first = True
-            for c in self.classes:
-                eng.vec_op(10, n, sd[c], x=pi[c])                          # D_c^1/2
-                B = Linv[c]
-                _chk(eng, lib.gpx_build_B(eng.h, eng._p(self.K), eng._p(sd[c]), n, npad, B.stride(0), eng._p(B)), "gpx_build_B")
-                dinv = eng.potrf(B)                                        # :93  L_c
-                eng.trtri(B, dinv, work)                                   # :94  L_c^-1 (kept for E_c matvecs)
-                eng.lauum(B, Ec)                                           # B_c^-1 (lower)
-                _chk(eng, lib.gpx_scale_sym_acc(eng.h, eng._p(Ec), eng._p(sd[c]), n, npad, Esum.stride(0), 0 if first else 1,
-                                                eng._p(Esum)), "gpx_scale_sym_acc")   # :95,:101
-                first = False
-            if first:  # this rank owns no class
+            ready = T.cuda.Event()
+            ready.record(main)
+            used = [False] * len(lanes)
+            for idx, c in enumerate(self.classes):
+                lane = lanes[idx % len(lanes)]
+                e = lane["eng"]
+                with T.cuda.stream(lane["stream"]):
+                    if not used[idx % len(lanes)]:
+                        lane["stream"].wait_event(ready)
+                    e.vec_op(10, n, sd[c], x=pi[c])                          # D_c^1/2
+                    B = Linv[c]
+                    e._sync_stream()
+                    _chk(e, lib.gpx_build_B(e.h, e._p(self.K), e._p(sd[c]), n, npad, B.stride(0), e._p(B)), "gpx_build_B")
+                    dinv = e.potrf_async(B)                                  # :93  L_c
+                    e.trtri(B, dinv, lane["work"])                           # :94  L_c^-1 (kept for E_c matvecs)
+                    e.lauum(B, lane["Ec"])                                   # B_c^-1 (lower)
+                    _chk(e, lib.gpx_scale_sym_acc(e.h, e._p(lane["Ec"]), e._p(sd[c]), n, npad, lane["Esum"].stride(0),
+                                                  1 if used[idx % len(lanes)] else 0, e._p(lane["Esum"])), "gpx_scale_sym_acc")   # :95,:101
+                    used[idx % len(lanes)] = True
+            for k, lane in enumerate(lanes):                                 # join: pivot status + stream order
+                if used[k]:
+                    with T.cuda.stream(lane["stream"]):
+                        lane["eng"].potrf_check()
+                    done = T.cuda.Event()
+                    done.record(lane["stream"])
+                    main.wait_event(done)
+            eng._sync_stream()
+            if not any(used):  # this rank owns no class
                 Esum.zero_()
+            for k in range(1, len(lanes)):
+                if used[k]:
+                    eng.vec_op(1, npad * npad, Esum, a=1.0, x=Esum, y=lanes[k]["Esum"])
             if self.allreduce is not None:
                 self.allreduce(Esum)
             M = Esum                                                       # factored in place, rebuilt next iteration

@@ -82,6 +82,11 @@ int gpx_cov_build(gpx_handle h, int kind, const double* X1, int64_t n1, const do
  * `dinv` (n/128 tiles of 128x128, device) receives the inverses of the diagonal blocks of L; they
  * are required by the solve / inverse routines below. */
 int gpx_potrf(gpx_handle h, double* A, int64_t n, int64_t lda, double* dinv);
+/* Same factorisation without the host synchronisation: returns after enqueueing; the first failing pivot of all
+ * gpx_potrf_async calls since the last query is fetched and cleared (with a stream synchronisation) by gpx_potrf_info.  Lets several handles
+ * (streams) factor independent matrices concurrently, e.g. the per-class B_c of GP_multi_classification.py:93. */
+int gpx_potrf_async(gpx_handle h, double* A, int64_t n, int64_t lda, double* dinv);
+int gpx_potrf_info(gpx_handle h, int* info_out);
 
 /* ---- A5: triangular solves (np.linalg.solve(L,.) / inv(L) call sites, row A5) -------------- */
 /* x <- L^-1 x (trans=0) or L^-T x (trans=1), one right-hand side, HBM-bound blocked TRSV. */

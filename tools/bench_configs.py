@@ -129,6 +129,8 @@ def main():
         Xd = eng.to_device(X)
         Kd = eng.cov(COV_SE, Xd, Xd, [1.0, 1.0], same_x=True)
         model = MultiLaplaceNewton(eng, Kd, C, n)
+        model.fit(y, tolerance=1e-6, max_iter=1)          # warm-up: allocations, extra handles / streams
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
         it = model.fit(y, tolerance=1e-6, max_iter=30)
         torch.cuda.synchronize()
