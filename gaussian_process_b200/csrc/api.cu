@@ -58,6 +58,7 @@ extern "C" int gpx_destroy(gpx_handle h) {
     cudaDeviceSynchronize();
     gpx_timing_destroy(h);
     if (h->scratch) cudaFree(h->scratch);
+    if (h->scratch2) cudaFree(h->scratch2);
     if (h->d_info) cudaFree(h->d_info);
     if (h->d_partial) cudaFree(h->d_partial);
     if (h->d_theta) cudaFree(h->d_theta);
@@ -102,6 +103,25 @@ int gpx_scratch(gpx_ctx* h, size_t bytes, void** out) {
     return 0;
 }
 
+int gpx_scratch2(gpx_ctx* h, size_t bytes, void** out) {
+    if (h->scratch2_bytes < bytes) {
+        if (h->scratch2) {
+            cudaStreamSynchronize(h->stream);
+            cudaFree(h->scratch2);
+            h->scratch2 = nullptr;
+            h->scratch2_bytes = 0;
+        }
+        cudaError_t e = cudaMalloc(&h->scratch2, bytes);
+        if (e != cudaSuccess) {
+            gpx_set_error("gpx: cudaMalloc(%zu) for scratch2 failed: %s", bytes, cudaGetErrorString(e));
+            return GPX_E_NOMEM;
+        }
+        h->scratch2_bytes = bytes;
+    }
+    *out = h->scratch2;
+    return 0;
+}
+
 int gpx_read_info(gpx_ctx* h, int* info_host) {
     GPX_CUDA(cudaMemcpyAsync(info_host, h->d_info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     GPX_CUDA(cudaStreamSynchronize(h->stream));
@@ -127,8 +147,21 @@ extern "C" int gpx_gp_fit(gpx_handle h, int kind, const double* X, int64_t n, in
     // alpha = L^-T (L^-1 y)                                   (tune...:308-309)
     GPX_CUDA(cudaMemsetAsync(alpha, 0, np_ * sizeof(double), h->stream));
     GPX_CUDA(cudaMemcpyAsync(alpha, y, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    GPX_TRY(gpx_trsv(h, A, np_, lda, dinv, 0, alpha));
-    GPX_TRY(gpx_trsv(h, A, np_, lda, dinv, 1, alpha));
+    const int bs = gpx_block_size_for(np_);
+    if (bs > GPX_T && np_ >= 2 * bs) {
+        // shorten the serial chain of the two solves with explicit inverses of the bs x bs diagonal blocks
+        void* sc = nullptr;
+        GPX_TRY(gpx_scratch2(h, ((size_t)np_ * bs + (size_t)np_ * bs / 4 + bs) * sizeof(double), &sc));
+        double* Dbig = (double*)sc;
+        double* work = Dbig + (size_t)np_ * bs;
+        double* tmp = work + (size_t)np_ * bs / 4;
+        GPX_TRY(gpx_block_inverses(h, A, np_, lda, dinv, bs, Dbig, work));
+        GPX_TRY(gpx_trsv_big(h, A, np_, lda, Dbig, bs, 0, alpha, tmp));
+        GPX_TRY(gpx_trsv_big(h, A, np_, lda, Dbig, bs, 1, alpha, tmp));
+    } else {
+        GPX_TRY(gpx_trsv(h, A, np_, lda, dinv, 0, alpha));
+        GPX_TRY(gpx_trsv(h, A, np_, lda, dinv, 1, alpha));
+    }
     int r = gpx_lml(h, A, n, lda, y, alpha, out3);           // tune...:312
     gpx_phase_mark(h, GPX_PH_END);
     return r;

@@ -14,6 +14,7 @@ struct gpx_ctx {
     int64_t launches;
     // scratch owned by the handle (grown on demand)
     void* scratch;       size_t scratch_bytes;
+    void* scratch2;      size_t scratch2_bytes;   // block inverses of the fused fit drivers
     int* d_info;         // device int: first failing pivot (1-based) or 0
     double* d_partial;   // reduction partials
     size_t partial_elems;
@@ -77,6 +78,7 @@ struct GemmArgs {
     int64_t lda, ldb, ldc;
     double alpha, beta;
     int64_t sA, sB, sC; int batch;   // strided batch (elements)
+    int64_t sA2, sB2, sC2; int batch2;  // optional outer batch level: blockIdx.z = z2 * batch + z1
     int a_kmajor, b_kmajor;     // 1: operand stored with k contiguous ([M][K] / [N][K]); 0: [K][M] / [K][N]
     int lower_only;             // skip output tiles strictly above the diagonal
     int kb_mode;                // first k: 0 -> 0, 1 -> tile row0, 2 -> tile col0, 3 -> block-cyclic mapped column position
@@ -104,4 +106,5 @@ int gpx_trsm_right_lt_block(gpx_ctx* h, double* B, int64_t m, int64_t ldb, const
 int gpx_trsm_left_prefix_block(gpx_ctx* h, const double* L, int64_t n, int64_t ldl, const double* dinv, double* B, int64_t ldb,
                                int P, int p, int nb);
 int gpx_scratch(gpx_ctx* h, size_t bytes, void** out);
+int gpx_scratch2(gpx_ctx* h, size_t bytes, void** out);
 int gpx_read_info(gpx_ctx* h, int* info_host);

@@ -85,12 +85,14 @@ __global__ void __launch_bounds__(Cfg<TN>::NT, Cfg<TN>::MIN_CTAS) dgemm_dmma_ker
     const int gpos = mapped_pos(p, col0);  // column position in global (block-cyclic) numbering
     const int brow0 = (p.cyc_P > 0 && !p.cyc_b_rows) ? col0 : gpos;  // offset of this column tile inside the B operand
     if (p.lower_only && gpos >= row0 + BM) return;                    // tile entirely above the diagonal
-    const double* __restrict__ A = p.A + (int64_t)blockIdx.z * p.sA;
-    const double* __restrict__ B = p.B + (int64_t)blockIdx.z * p.sB;
-    double* C = p.C + (int64_t)blockIdx.z * p.sC;
+    const int z1 = p.batch2 > 1 ? (int)(blockIdx.z % p.batch) : (int)blockIdx.z;
+    const int z2 = p.batch2 > 1 ? (int)(blockIdx.z / p.batch) : 0;
+    const double* __restrict__ A = p.A + (int64_t)z1 * p.sA + (int64_t)z2 * p.sA2;
+    const double* __restrict__ B = p.B + (int64_t)z1 * p.sB + (int64_t)z2 * p.sB2;
+    double* C = p.C + (int64_t)z1 * p.sC + (int64_t)z2 * p.sC2;
 
     int kbeg = (p.kb_mode == 1 ? row0 : (p.kb_mode == 2 ? (col0 / 128) * 128 : (p.kb_mode == 3 ? (gpos / 128) * 128 : 0))) +
-               (int)(blockIdx.z * p.kb_batch) + p.kb_const;
+               (int)(z1 * p.kb_batch) + p.kb_const;
     if (kbeg < 0) kbeg = 0;
     int kend = p.ke_mode == 1 ? row0 + BM : (p.ke_mode == 2 ? (col0 / 128) * 128 + 128 : p.K);
     if (kend > p.K) kend = p.K;
@@ -198,7 +200,7 @@ double exec_flops(const GemmArgs& a, int TN) {
                 if (ke > kbz) ksum += (double)(ke - kbz);
             }
         }
-    return 2.0 * BM * TN * ksum;
+    return 2.0 * BM * TN * ksum * (a.batch2 > 1 ? a.batch2 : 1);
 }
 
 template <bool A_KM, bool B_KM, int TN>
@@ -210,7 +212,7 @@ int launch_t(gpx_ctx* h, const GemmArgs& a) {
         GPX_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<A_KM, B_KM, TN>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         configured = true;
     }
-    dim3 grid(a.N / TN, a.M / BM, a.batch > 0 ? a.batch : 1);
+    dim3 grid(a.N / TN, a.M / BM, (a.batch > 0 ? a.batch : 1) * (a.batch2 > 1 ? a.batch2 : 1));
     if (h->timing_on) gpx_timing_gemm_begin(h, exec_flops(a, TN));
     dgemm_dmma_kernel<A_KM, B_KM, TN><<<grid, C_::NT, C_::SMEM, h->stream>>>(a);
     GPX_CHECK_LAUNCH(h);

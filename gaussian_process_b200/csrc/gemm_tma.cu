@@ -270,7 +270,7 @@ int make_map(CUtensorMap* m, const double* ptr, int64_t rows, int64_t K, int64_t
 
 // Returns 1 if the launch was done through the TMA kernel, 0 if the caller must use the cp.async kernel, <0 on error.
 int gpx_gemm_tma_try_launch(gpx_ctx* h, const GemmArgs& a, double flops_exec) {
-    if (a.batch > 1 || a.C == a.A || a.C == a.B) return 0;
+    if (a.batch > 1 || a.batch2 > 1 || a.C == a.A || a.C == a.B) return 0;
     if ((a.lda % 2) || (a.ldb % 2)) return 0;
     if (tma_init() != 1) return 0;
     constexpr int TN = 64;

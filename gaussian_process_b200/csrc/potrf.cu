@@ -716,3 +716,135 @@ int gpx_trsm_left_prefix_block(gpx_ctx* h, const double* L, int64_t n, int64_t l
 extern "C" int gpx_debug_leaf_cycles(long long* out4) {
     return cudaMemcpyFromSymbol(out4, g_leaf_dbg, 4 * sizeof(long long)) == cudaSuccess ? 0 : GPX_E_CUDA;
 }
+
+// ---- block inverses: explicit inverses of the bs x bs diagonal blocks of L (bs = 128 * 2^k <= 1024) ---------------
+// They shorten the serial chain of every triangular solve by bs/128: a blocked TRSV / TRSM then has n/bs sequential
+// steps, each a full-width GEMV / GEMM with an explicit block inverse.  Built from the 128-leaf inverses with the
+// level-synchronous scheme of trtri_levels, batched over (sub-problem, block).
+namespace {
+__global__ void place_leaf_inverses_kernel(double* __restrict__ D, int bs, const double* __restrict__ dinv) {
+    const int t = blockIdx.x, lpb = bs / LT;               // leaf index, leaves per block
+    double* dst = D + (int64_t)(t / lpb) * bs * bs + (int64_t)(t % lpb) * LT * (bs + 1);
+    const double* src = dinv + (int64_t)t * LT * LT;
+    for (int idx = threadIdx.x; idx < LT * LT; idx += blockDim.x) dst[(int64_t)(idx >> 7) * bs + (idx & 127)] = src[idx];
+}
+}  // namespace
+
+extern "C" int gpx_block_size_for(int64_t n) {
+    for (int bs = 1024; bs > LT; bs >>= 1)
+        if (n % bs == 0) return bs;
+    return LT;
+}
+
+// D: (n/bs) blocks of bs x bs doubles; work: n*bs/4 doubles.
+extern "C" int gpx_block_inverses(gpx_handle h, const double* L, int64_t n, int64_t ldl, const double* dinv, int bs, double* D,
+                                  double* work) {
+    GPX_REQUIRE(h != nullptr, 1);
+    GPX_REQUIRE(n > 0 && n % bs == 0 && bs >= LT && bs % LT == 0 && (bs & (bs - 1)) == 0, 6);
+    const int nB = (int)(n / bs);
+    GPX_CUDA(cudaMemsetAsync(D, 0, (size_t)n * bs * sizeof(double), h->stream));
+    place_leaf_inverses_kernel<<<(unsigned)(n / LT), 256, 0, h->stream>>>(D, bs, dinv);
+    GPX_CHECK_LAUNCH(h);
+    for (int64_t hs = LT; hs < bs; hs *= 2) {
+        const int per = (int)(bs / (2 * hs));
+        GemmArgs a = base_args();   // T = L21 * X11   (k >= column tile)
+        a.A = L + hs * ldl; a.lda = ldl; a.a_kmajor = 1; a.sA = 2 * hs * (ldl + 1); a.sA2 = (int64_t)bs * (ldl + 1);
+        a.B = D; a.ldb = bs; a.b_kmajor = 0; a.sB = 2 * hs * (bs + 1); a.sB2 = (int64_t)bs * bs;
+        a.C = work; a.ldc = hs; a.sC = hs * hs; a.sC2 = (int64_t)per * hs * hs;
+        a.M = (int)hs; a.N = (int)hs; a.K = (int)hs;
+        a.batch = per; a.batch2 = nB;
+        a.kb_mode = 2;
+        GPX_TRY(gpx_gemm_launch(h, a));
+        GemmArgs b = base_args();   // X21 = -X22 * T   (k <= row tile)
+        b.A = D + hs * (bs + 1); b.lda = bs; b.a_kmajor = 1; b.sA = 2 * hs * (bs + 1); b.sA2 = (int64_t)bs * bs;
+        b.B = work; b.ldb = hs; b.b_kmajor = 0; b.sB = hs * hs; b.sB2 = (int64_t)per * hs * hs;
+        b.C = D + hs * bs; b.ldc = bs; b.sC = 2 * hs * (bs + 1); b.sC2 = (int64_t)bs * bs;
+        b.M = (int)hs; b.N = (int)hs; b.K = (int)hs;
+        b.batch = per; b.batch2 = nB;
+        b.alpha = -1.0;
+        b.ke_mode = 1;
+        b.rev_rows = 1;
+        GPX_TRY(gpx_gemm_launch(h, b));
+    }
+    return 0;
+}
+
+namespace {
+// x <- L^-1 x / L^-T x with bs-block inverses; tmp: bs doubles
+int trsv_big_rec(gpx_ctx* h, const double* L, int64_t n, int64_t ldl, const double* D, int bs, int trans, double* x, double* tmp) {
+    if (n == bs) {
+        GPX_TRY(gpx_gemv(h, trans, bs, bs, 1.0, D, bs, x, 0.0, tmp));
+        GPX_CUDA(cudaMemcpyAsync(x, tmp, (size_t)bs * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        return 0;
+    }
+    const int64_t h1 = ((n / bs) / 2) * bs, h2 = n - h1;
+    const double* L21 = L + h1 * ldl;
+    const double* L22 = L21 + h1;
+    const double* D2 = D + (h1 / bs) * (int64_t)bs * bs;
+    if (!trans) {
+        GPX_TRY(trsv_big_rec(h, L, h1, ldl, D, bs, 0, x, tmp));
+        GPX_TRY(gpx_gemv(h, 0, h2, h1, -1.0, L21, ldl, x, 1.0, x + h1));
+        return trsv_big_rec(h, L22, h2, ldl, D2, bs, 0, x + h1, tmp);
+    }
+    GPX_TRY(trsv_big_rec(h, L22, h2, ldl, D2, bs, 1, x + h1, tmp));
+    GPX_TRY(gpx_gemv(h, 1, h2, h1, -1.0, L21, ldl, x + h1, 1.0, x));
+    return trsv_big_rec(h, L, h1, ldl, D, bs, 1, x, tmp);
+}
+
+// B <- L^-1 B / L^-T B (B is n x m, row-major); tmp: bs * m doubles
+int trsm_big_rec(gpx_ctx* h, const double* L, int64_t n, int64_t ldl, const double* D, int bs, int trans, double* B, int64_t m,
+                 int64_t ldb, double* tmp) {
+    if (n == bs) {
+        GemmArgs a = base_args();   // tmp = D B  or  D^T B  (triangular k range), then copied back
+        a.A = D; a.lda = bs; a.a_kmajor = trans ? 0 : 1;
+        a.B = B; a.ldb = ldb; a.b_kmajor = 0;
+        a.C = tmp; a.ldc = m;
+        a.M = bs; a.N = (int)m; a.K = bs;
+        if (trans) a.kb_mode = 1; else { a.ke_mode = 1; a.rev_rows = 1; }
+        GPX_TRY(gpx_gemm_launch(h, a));
+        GPX_CUDA(cudaMemcpy2DAsync(B, ldb * sizeof(double), tmp, m * sizeof(double), m * sizeof(double), bs,
+                                   cudaMemcpyDeviceToDevice, h->stream));
+        return 0;
+    }
+    const int64_t h1 = ((n / bs) / 2) * bs, h2 = n - h1;
+    const double* L21 = L + h1 * ldl;
+    const double* L22 = L21 + h1;
+    const double* D2 = D + (h1 / bs) * (int64_t)bs * bs;
+    double* B2 = B + h1 * ldb;
+    if (!trans) {
+        GPX_TRY(trsm_big_rec(h, L, h1, ldl, D, bs, 0, B, m, ldb, tmp));
+        GemmArgs a = base_args();   // B2 -= L21 X1
+        a.A = L21; a.lda = ldl; a.a_kmajor = 1;
+        a.B = B; a.ldb = ldb; a.b_kmajor = 0;
+        a.C = B2; a.ldc = ldb;
+        a.M = (int)h2; a.N = (int)m; a.K = (int)h1;
+        a.alpha = -1.0; a.beta = 1.0;
+        GPX_TRY(gpx_gemm_launch(h, a));
+        return trsm_big_rec(h, L22, h2, ldl, D2, bs, 0, B2, m, ldb, tmp);
+    }
+    GPX_TRY(trsm_big_rec(h, L22, h2, ldl, D2, bs, 1, B2, m, ldb, tmp));
+    GemmArgs a = base_args();   // B1 -= L21^T X2
+    a.A = L21; a.lda = ldl; a.a_kmajor = 0;
+    a.B = B2; a.ldb = ldb; a.b_kmajor = 0;
+    a.C = B; a.ldc = ldb;
+    a.M = (int)h1; a.N = (int)m; a.K = (int)h2;
+    a.alpha = -1.0; a.beta = 1.0;
+    GPX_TRY(gpx_gemm_launch(h, a));
+    return trsm_big_rec(h, L, h1, ldl, D, bs, 1, B, m, ldb, tmp);
+}
+}  // namespace
+
+extern "C" int gpx_trsv_big(gpx_handle h, const double* L, int64_t n, int64_t ldl, const double* D, int bs, int trans, double* x,
+                            double* tmp) {
+    GPX_REQUIRE(h != nullptr, 1);
+    GPX_REQUIRE(n > 0 && n % bs == 0, 3);
+    return trsv_big_rec(h, L, n, ldl, D, bs, trans, x, tmp);
+}
+
+extern "C" int gpx_trsm_big(gpx_handle h, const double* L, int64_t n, int64_t ldl, const double* D, int bs, int trans, double* B,
+                            int64_t nrhs, int64_t ldb, double* tmp) {
+    GPX_REQUIRE(h != nullptr, 1);
+    GPX_REQUIRE(n > 0 && n % bs == 0, 3);
+    GPX_REQUIRE(nrhs > 0 && nrhs % LT == 0, 9);
+    return trsm_big_rec(h, L, n, ldl, D, bs, trans, B, nrhs, ldb, tmp);
+}

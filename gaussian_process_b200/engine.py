@@ -47,6 +47,7 @@ class GPFit:
     grad: Optional[np.ndarray] = None
     Kinv: "object" = None
     L_is_inverse: bool = False
+    big: "object" = None  # (D, bs): explicit inverses of the bs x bs diagonal blocks of L (lazy, for prediction)
 
 
 class Engine:
@@ -163,8 +164,39 @@ class Engine:
                                 B.shape[1], B.stride(0)), "gpx_trsm")
         return B
 
-    def potrs_vec(self, L, dinv, x):
-        """x <- (L L^T)^-1 x."""
+    def block_inverses(self, L, dinv):
+        """Explicit inverses of the bs x bs diagonal blocks of L (bs up to 1024) -> (D, bs) or (None, 128) when the
+        matrix is too small to benefit.  They shorten the serial chain of trsv / trsm by bs/128."""
+        self._sync_stream()
+        n = L.shape[0]
+        bs = int(self.lib.gpx_block_size_for(n))
+        if bs <= GPX_TILE or n < 2 * bs:
+            return None, GPX_TILE
+        D = self.empty(n // bs, bs, bs)
+        work = self.empty(n * bs // 4)
+        check(self.lib.gpx_block_inverses(self.h, self._p(L), n, L.stride(0), self._p(dinv), bs, self._p(D), self._p(work)),
+              "gpx_block_inverses")
+        return D, bs
+
+    def trsv_big(self, L, D, bs, x, trans: bool = False):
+        self._sync_stream()
+        tmp = self.empty(bs)
+        check(self.lib.gpx_trsv_big(self.h, self._p(L), L.shape[0], L.stride(0), self._p(D), bs, int(trans), self._p(x), self._p(tmp)),
+              "gpx_trsv_big")
+        return x
+
+    def trsm_big(self, L, D, bs, B, trans: bool = False):
+        self._sync_stream()
+        tmp = self.empty(bs * B.shape[1])
+        check(self.lib.gpx_trsm_big(self.h, self._p(L), L.shape[0], L.stride(0), self._p(D), bs, int(trans), self._p(B), B.shape[1],
+                                    B.stride(0), self._p(tmp)), "gpx_trsm_big")
+        return B
+
+    def potrs_vec(self, L, dinv, x, big=None):
+        """x <- (L L^T)^-1 x.  ``big`` = (D, bs) from block_inverses() uses the short-chain solves."""
+        if big is not None and big[0] is not None:
+            self.trsv_big(L, big[0], big[1], x, False)
+            return self.trsv_big(L, big[0], big[1], x, True)
         self.trsv(L, dinv, x, False)
         return self.trsv(L, dinv, x, True)
 
@@ -284,7 +316,12 @@ class Engine:
         lib = self.lib
         check(lib.gpx_predict_moments(self.h, self._p(Ks), None, fit.n, m, Ks.stride(0), self._p(fit.alpha), None,
                                       self._p(mu), None), "gpx_predict_moments(mu)")
-        self.trsm(fit.L, fit.dinv, Ks, trans=False)                          # Ks <- V = L^-1 K_s
+        if getattr(fit, "big", None) is None:
+            fit.big = self.block_inverses(fit.L, fit.dinv)
+        if fit.big[0] is not None:
+            self.trsm_big(fit.L, fit.big[0], fit.big[1], Ks, trans=False)    # Ks <- V = L^-1 K_s (short chain)
+        else:
+            self.trsm(fit.L, fit.dinv, Ks, trans=False)                      # Ks <- V = L^-1 K_s
         if kss_diag is None:
             Kss = self.cov(fit.kind, Xsd, Xsd, fit.theta, same_x=True)
             kss_diag = self.diag(Kss, m)

@@ -65,7 +65,7 @@ class BinaryLaplace:
             u = eng.gemv(Linv, t, eng.zeros(npad), m=n, n=n)
             t = eng.gemv(Linv, u, eng.zeros(npad), trans=True, m=n, n=n)
         else:
-            eng.potrs_vec(L, dinv, t)
+            eng.potrs_vec(L, dinv, t, big=eng.block_inverses(L, dinv))
         a = eng.vec_op(3, n, eng.zeros(npad), x=b, y=sw, z=t)
         f_new = eng.gemv(self.K, a, eng.zeros(npad), m=n, n=n)
         d = eng.vec_op(6, n, eng.zeros(npad), x=f_new, y=f)

@@ -94,6 +94,14 @@ int gpx_trsv(gpx_handle h, const double* L, int64_t n, int64_t ldl, const double
 /* B <- L^-1 B (trans=0) or L^-T B (trans=1); B is n x nrhs row-major, nrhs % 128 == 0. */
 int gpx_trsm(gpx_handle h, const double* L, int64_t n, int64_t ldl, const double* dinv, int trans,
              double* B, int64_t nrhs, int64_t ldb);
+/* Explicit inverses of the bs x bs diagonal blocks of L (bs = gpx_block_size_for(n): 1024, 512, 256 or 128) built from
+ * the leaf inverses; D holds n/bs blocks of bs x bs doubles, work n*bs/4 doubles.  gpx_trsv_big / gpx_trsm_big are the
+ * same solves as gpx_trsv / gpx_trsm with a bs/128 times shorter serial chain (tmp: bs, resp. bs*nrhs doubles). */
+int gpx_block_size_for(int64_t n);
+int gpx_block_inverses(gpx_handle h, const double* L, int64_t n, int64_t ldl, const double* dinv, int bs, double* D, double* work);
+int gpx_trsv_big(gpx_handle h, const double* L, int64_t n, int64_t ldl, const double* D, int bs, int trans, double* x, double* tmp);
+int gpx_trsm_big(gpx_handle h, const double* L, int64_t n, int64_t ldl, const double* D, int bs, int trans, double* B,
+                 int64_t nrhs, int64_t ldb, double* tmp);
 /* In-place inverse of the lower-triangular factor: L <- L^-1 (np.linalg.inv(L), tune...:144).
  * `work` must hold n*n/4 doubles. */
 int gpx_trtri(gpx_handle h, double* L, int64_t n, int64_t ldl, const double* dinv, double* work);

@@ -157,3 +157,28 @@ def test_fp64_peak_microbench_runs(eng):
     tf_dmma, _ = eng.fp64_peak(True, 512)
     tf_dfma, _ = eng.fp64_peak(False, 512)
     assert tf_dmma > 1.0 and tf_dfma > 1.0
+
+
+@pytest.mark.parametrize("n", [2048, 2560, 3072])
+def test_block_inverses_and_short_chain_solves(eng, n):
+    A = spd(n, seed=n + 1)
+    L = np.linalg.cholesky(A)
+    Ad = eng.to_device(A)
+    dinv = eng.potrf(Ad)
+    D, bs = eng.block_inverses(Ad, dinv)
+    assert D is not None and n % bs == 0
+    Dh = eng.to_host(D)
+    for b in range(n // bs):
+        blk = L[b * bs:(b + 1) * bs, b * bs:(b + 1) * bs]
+        assert rel(Dh[b] @ blk, np.eye(bs)) < 1e-10
+        assert np.all(np.triu(Dh[b], 1) == 0.0)
+    rs = np.random.RandomState(1)
+    b0 = rs.randn(n)
+    for trans in (False, True):
+        x = eng.to_device(b0.copy())
+        eng.trsv_big(Ad, D, bs, x, trans=trans)
+        assert rel(eng.to_host(x), np.linalg.solve(L.T if trans else L, b0)) < 1e-10
+        Bm = rs.randn(n, 256)
+        Xd = eng.to_device(Bm.copy())
+        eng.trsm_big(Ad, D, bs, Xd, trans=trans)
+        assert rel(eng.to_host(Xd), np.linalg.solve(L.T if trans else L, Bm)) < 1e-10
