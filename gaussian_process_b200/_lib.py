@@ -29,6 +29,7 @@ class GpxError(RuntimeError):
 _CTYPES = {
     "int": ctypes.c_int,
     "int64_t": ctypes.c_int64,
+    "long long": ctypes.c_longlong,
     "double": ctypes.c_double,
     "void": None,
     "const char*": ctypes.c_char_p,
@@ -41,6 +42,7 @@ def _ctype_of(decl: str):
     decl = decl.strip()
     decl = re.sub(r"\s+", " ", decl)
     # drop the parameter name
+    decl = decl.replace("long long", "longlong")
     m = re.match(r"^(const )?(\w+)\s*(\*?)\s*(\w+)?$", decl)
     if not m:
         raise ValueError("cannot parse parameter %r" % decl)

@@ -189,6 +189,9 @@ int gpx_bench_fp64_peak(gpx_handle h, int use_dmma, int iters, double* tflops_ou
 int gpx_timing_enable(gpx_handle h, int on);
 int gpx_timing_collect(gpx_handle h, double* out, int nout);
 
+/* debug hook: cycles spent by the last potrf leaf kernel in {load, factor, inverse, store} (clock64) */
+int gpx_debug_leaf_cycles(long long* out4);
+
 /* ---- multi-GPU (one process per GPU; NCCL communicator owned by the handle) -----------------
  * Layout: 1-D block-cyclic block columns of width nb (a P x 1 grid of the 2-D block-cyclic scheme), panels
  * broadcast with NCCL and kept in a replicated factor; see nccl_mg.cu.  NCCL is dlopen'ed at run time. */
