@@ -46,12 +46,20 @@ potrf_leaf_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ Dinv
     global_off += blockIdx.x * LT;
     const int tid = threadIdx.x;
     const long long t_start = clock64();
-    int bi = -1, bj = -1;
+    // Factorisation phase: blocks are numbered COLUMN-major (all blocks of block column 0, then column 1, ...), so the
+    // threads that still have work at step p (bj > p) are a contiguous tail of the CTA -- finished warps skip the step
+    // entirely -- and the panel threads (bj == p+1) sit in one or two warps instead of one lane in each of 17 warps.
+    // Inverse phase: ROW-major numbering (ri, rj), for the same reason applied to block rows.
+    int bi = -1, bj = -1, ri = -1, rj = -1;
     if (tid < NBK * (NBK + 1) / 2) {
-        bi = (int)((sqrtf(8.f * tid + 1.f) - 1.f) * 0.5f);
-        while (bi * (bi + 1) / 2 > tid) --bi;
-        while ((bi + 1) * (bi + 2) / 2 <= tid) ++bi;
-        bj = tid - bi * (bi + 1) / 2;
+        int c = 0, off = 0;
+        while (off + (NBK - c) <= tid) { off += NBK - c; ++c; }
+        bj = c;
+        bi = c + (tid - off);
+        ri = (int)((sqrtf(8.f * tid + 1.f) - 1.f) * 0.5f);
+        while (ri * (ri + 1) / 2 > tid) --ri;
+        while ((ri + 1) * (ri + 2) / 2 <= tid) ++ri;
+        rj = tid - ri * (ri + 1) / 2;
     }
     const bool active = bi >= 0;
     double a[LB][LB];
@@ -196,22 +204,22 @@ potrf_leaf_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ Dinv
 #pragma unroll
         for (int c = 0; c < LB; ++c) acc[r][c] = 0.0;
     for (int k = 0; k + 1 < NBK; ++k) {
-        if (active && bi > k && bj <= k) {
+        if (active && ri > k && rj <= k) {
             double li[LB][LB], xt[LB][LB];     // xt[c][m] = X_kj[m][c]
 #pragma unroll
             for (int r = 0; r < LB; ++r) {
-                const double2* pi_ = reinterpret_cast<const double2*>(S + soff(LB * bi + r, LB * k));
+                const double2* pi_ = reinterpret_cast<const double2*>(S + soff(LB * ri + r, LB * k));
                 double2 u0 = pi_[0], u1 = pi_[1];
                 li[r][0] = u0.x; li[r][1] = u0.y; li[r][2] = u1.x; li[r][3] = u1.y;
             }
-            if (bj < k) {
+            if (rj < k) {
 #pragma unroll
                 for (int c = 0; c < LB; ++c) {
-                    const double2* px = reinterpret_cast<const double2*>(S + soff(LB * bj + c, LB * k));
+                    const double2* px = reinterpret_cast<const double2*>(S + soff(LB * rj + c, LB * k));
                     double2 u0 = px[0], u1 = px[1];
                     xt[c][0] = u0.x; xt[c][1] = u0.y; xt[c][2] = u1.x; xt[c][3] = u1.y;
                 }
-            } else {  // bj == k: X_kk (lower triangular)
+            } else {  // rj == k: X_kk (lower triangular)
 #pragma unroll
                 for (int c = 0; c < LB; ++c)
 #pragma unroll
@@ -224,7 +232,7 @@ potrf_leaf_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ Dinv
                 for (int r = 0; r < LB; ++r)
 #pragma unroll
                     for (int c = 0; c < LB; ++c) acc[r][c] = fma(li[r][m], xt[c][m], acc[r][c]);
-            if (bi == k + 1) {                 // row k+1 is complete for every j <= k: finalise and publish (transposed)
+            if (ri == k + 1) {                 // row k+1 is complete for every j <= k: finalise and publish (transposed)
                 const int kk = k + 1;
                 double x[LB][LB];
 #pragma unroll
@@ -243,7 +251,7 @@ potrf_leaf_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ Dinv
                         for (int m = 0; m <= r; ++m) v += x[r][m] * acc[m][c];
                         o[r] = -v;
                     }
-                    double2* dst = reinterpret_cast<double2*>(S + soff(LB * bj + c, LB * kk));
+                    double2* dst = reinterpret_cast<double2*>(S + soff(LB * rj + c, LB * kk));
                     dst[0] = make_double2(o[0], o[1]);
                     dst[1] = make_double2(o[2], o[3]);
                 }
