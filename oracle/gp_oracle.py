@@ -193,6 +193,41 @@ def rbf_fit_lml_grad(X_train, y_train, sigma, l, s=S_NOISE, chunk=None):
     return lml, rbf_grad_l(X_train, sigma, l, alpha, K_y_inv, chunk), alpha
 
 
+def rbf_fit_lml_grad_best_effort(X_train, y_train, sigma, l, s=S_NOISE, chunk=2048, timings=None):
+    """Memory-feasible "best-effort CPU" variant of the same unit: the same quantities as
+    `rbf_fit_lml_grad` (tune...:123-145) computed the LAPACK-aware way -- chunked kernel, dpotrf,
+    triangular dpotrs, dpotri and the O(N^2) trace  .5 * sum((alpha alpha^T - K^-1) o dK/dl)  instead of
+    the reference's LU solves, two dense inverses and the N^3 GEMM of tune...:55.  It is a timing baseline
+    only (bench.py `cpu_best_effort`); parity is always taken against `rbf_fit_lml_grad`.  `timings`, when a
+    dict, receives the seconds of the O(N^2 D) part ("n2") and of the O(N^3) part ("n3") so that a bounded
+    sample can be scaled term by term."""
+    import time
+    from scipy.linalg import cho_factor, cho_solve, lapack
+    n = len(X_train)
+    t0 = time.perf_counter()
+    d = sqdist(X_train, X_train, chunk)
+    K = sigma ** 2 * np.exp(-.5 * d / (l ** 2))
+    dK = K * (d / l ** 3)                                                 # tune...:54
+    del d
+    K[np.diag_indices(n)] += s
+    t1 = time.perf_counter()
+    c, low = cho_factor(K, lower=True, overwrite_a=True, check_finite=False)
+    alpha = cho_solve((c, low), y_train, check_finite=False)
+    lml = -.5 * np.dot(y_train, alpha) - np.log(np.diagonal(c)).sum() - n / 2.0 * np.log(2 * np.pi)
+    Kinv, info = lapack.dpotri(c, lower=1, overwrite_c=1)
+    if info != 0:
+        raise np.linalg.LinAlgError("dpotri info=%d" % info)
+    t2 = time.perf_counter()
+    # only the lower triangle of Kinv is valid: tr(Kinv dK) = 2 * sum(tril(Kinv o dK), -1) + diag part
+    prod = np.tril(Kinv) * dK
+    tr_kinv = 2.0 * prod.sum() - np.diagonal(prod).sum()
+    grad = .5 * (np.dot(alpha, np.dot(dK, alpha)) - tr_kinv)
+    if timings is not None:
+        timings["n3"] = t2 - t1
+        timings["n2"] = (t1 - t0) + (time.perf_counter() - t2)
+    return lml, grad, alpha
+
+
 def tune_first(X_train, X_test, y_train, num_fun, sigma, l, max_iter=10000, tolerance=0.001):
     """tune_hyperparms_regression.py:104-162 without the prints: gradient ascent on l until
     |dLML| <= 1e-3 -> (mu, sd, f_post, lml, l, iterations)."""

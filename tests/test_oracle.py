@@ -65,6 +65,11 @@ def test_golden_ka2_lml_grad(golden):
     Kinv = np.dot(np.linalg.inv(L.T), np.linalg.inv(L))
     gh = O.lml_grad_from(alpha, Kinv, O.rbf_dcov(X, 1.0, 4.0))
     assert rel(gh[1], g["dlml_dl"]) < 1e-9
+    # the "best-effort CPU" timing baseline (dpotrf/dpotri, O(N^2) trace) computes the same numbers
+    tm = {}
+    lml_b, grad_b, alpha_b = O.rbf_fit_lml_grad_best_effort(X, y, 1.0, 4.0, chunk=100, timings=tm)
+    assert rel(lml_b, g["lml"]) < RTOL and rel(grad_b, g["dlml_dl"]) < 1e-9 and rel(alpha_b, g["alpha"]) < 1e-9
+    assert tm["n2"] > 0 and tm["n3"] > 0
 
 
 def test_golden_ka2_tune_and_bo(golden):
