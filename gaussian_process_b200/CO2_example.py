@@ -60,6 +60,10 @@ def bayesian_opt(hyperparms_train, hyperparms_test, y_train):
     (CO2...:152-179) -> (mu_post, stand_devi)."""
     eng = get_engine()
     hp = _theta(np.asarray(hyperparms_train)[0])
+    if _gpr.FUSED_SMALL_PATH and len(hyperparms_train) <= eng.small_max():
+        mu, var, _, _ = eng.small_posterior(COV_CO2, hyperparms_train, y_train, hyperparms_test, hp, BO_NOISE, 0.0, None)
+        with np.errstate(invalid="ignore"):
+            return mu, np.sqrt(var)
     fit = eng.fit(COV_CO2, np.asarray(hyperparms_train, dtype=np.float64), y_train, hp, BO_NOISE)
     mu, var, _ = eng.predict(fit, np.asarray(hyperparms_test, dtype=np.float64))
     with np.errstate(invalid="ignore"):

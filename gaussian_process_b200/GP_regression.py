@@ -15,6 +15,7 @@ from .engine import get_engine
 
 NOISE_VARIANCE = 0.0005      # `s` of GP_regression.py:58,81,120
 SAMPLING_JITTER = 1e-6       # GP_regression.py:154
+FUSED_SMALL_PATH = True      # N <= 128 and n <= 128: one-launch posterior (csrc/small.cu); False forces the tiled path
 
 # module globals the reference drivers read (GP_regression.py:105,286,295)
 n = 100
@@ -94,7 +95,18 @@ def _fit_predict_sample(kind, theta, s, X_train, X_test, y_train, num_fun):
     """fit -> (mu, sd, f_post) shared by every regression-style entry point
     (GP_regression.py:138-156; tune...:85-101; CO2...:198-214)."""
     eng = get_engine()
-    fit = eng.fit(kind, np.asarray(X_train, dtype=np.float64), y_train, theta, s)
+    X_train = np.asarray(X_train, dtype=np.float64)
+    X_test = np.asarray(X_test, dtype=np.float64)
+    if FUSED_SMALL_PATH and num_fun >= 1 and X_train.shape[0] <= eng.small_max() and X_test.shape[0] <= eng.small_max():
+        # as-shipped sizes (N=5, n=100): the whole linear algebra is ONE kernel launch (csrc/small.cu) that leaves
+        # the sampling factor on the device; the normals are drawn afterwards, as in the reference (:155 comes after
+        # the Cholesky calls that may raise), and a second tiny launch forms mu + L_ z.
+        mu_post, var, _ = eng.small_fit(kind, X_train, y_train, X_test, theta, s, SAMPLING_JITTER)
+        with np.errstate(invalid="ignore"):
+            stand_devi = np.sqrt(var)                       # NaN where var < 0, as in the reference
+        z = np.random.normal(size=(X_test.shape[0], num_fun))
+        return mu_post, stand_devi, eng.small_sample(X_test.shape[0], z), None
+    fit = eng.fit(kind, X_train, y_train, theta, s)
     Xs = eng.to_device(np.asarray(X_test, dtype=np.float64))
     m = Xs.shape[0]
     mu, var, V = eng.predict(fit, Xs, want_v=True)

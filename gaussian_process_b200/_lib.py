@@ -19,7 +19,7 @@ HEADER_PATH = os.path.join(_ROOT, "include", "gpx.h")
 
 GPX_TILE = 128
 COV_SE, COV_LIN, COV_PER, COV_CO2 = 0, 1, 2, 3
-COV_SAME_X, COV_LOWER = 1, 2
+COV_SAME_X, COV_LOWER, COV_DELTA = 1, 2, 4
 
 
 class GpxError(RuntimeError):

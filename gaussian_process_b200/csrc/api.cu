@@ -59,6 +59,8 @@ extern "C" int gpx_destroy(gpx_handle h) {
     gpx_timing_destroy(h);
     if (h->scratch) cudaFree(h->scratch);
     if (h->scratch2) cudaFree(h->scratch2);
+    if (h->pinned) cudaFreeHost(h->pinned);
+    if (h->d_small) cudaFree(h->d_small);
     if (h->d_info) cudaFree(h->d_info);
     if (h->d_partial) cudaFree(h->d_partial);
     if (h->d_theta) cudaFree(h->d_theta);

@@ -15,6 +15,8 @@ struct gpx_ctx {
     // scratch owned by the handle (grown on demand)
     void* scratch;       size_t scratch_bytes;
     void* scratch2;      size_t scratch2_bytes;   // block inverses of the fused fit drivers
+    void* pinned;        size_t pinned_bytes;     // host staging buffer of the host-pointer entry points (small.cu)
+    double* d_small;     int small_n;             // posterior factor kept by gpx_gp_small_fit_host (small.cu)
     int* d_info;         // device int: first failing pivot (1-based) or 0
     double* d_partial;   // reduction partials
     size_t partial_elems;

@@ -8,77 +8,13 @@
 // lml_grad  : reads K^-1 once (lower tiles), recomputes dK/dtheta_j per element from X and accumulates
 //             .5 * sum (alpha_i alpha_j - Kinv_ij) dK_ij for all theta at once.  HBM-read bound.
 #include "common.cuh"
+#include "cov_eval.cuh"
 
 namespace {
 
+using namespace gpx_cov;
+
 constexpr int TM = 128, TN = 128, DCH = 16, CTHREADS = 512, RI = 8;  // thread owns RI x 4 outputs
-constexpr double PI_D = 3.141592653589793238462643383279502884;  // == np.pi
-
-struct CovParams {
-    int kind, ntheta, D;
-    double th[11];
-};
-
-template <int KIND>
-struct NTheta { static constexpr int value = KIND == GPX_COV_SE ? 2 : KIND == GPX_COV_LIN ? 1 : KIND == GPX_COV_PER ? 2 : 11; };
-
-// value and derivatives of one covariance entry.  `acc` is the squared distance (or, for LIN, the
-// centred dot product); `aux` is sum_d (a_d + b_d) for LIN's derivative; diag = (same_x && i == j).
-template <int KIND, bool WITH_DK>
-__device__ __forceinline__ double cov_eval(const CovParams& p, double acc, double aux, bool diag, double* dk) {
-    if (KIND == GPX_COV_SE) {
-        const double sigma = p.th[0], l = p.th[1];
-        const double e = exp(-.5 * (1.0 / (l * l)) * acc);  // GP_regression.py:19
-        if (WITH_DK) {
-            dk[0] = 2.0 * sigma * e;                          // tune...:48
-            dk[1] = (sigma * sigma) * e * (acc / (l * l * l));  // tune...:54
-        }
-        return (sigma * sigma) * e;
-    } else if (KIND == GPX_COV_LIN) {
-        if (WITH_DK) dk[0] = -(aux - 2.0 * p.D * p.th[0]);
-        return acc;                                           // GP_regression.py:32
-    } else if (KIND == GPX_COV_PER) {
-        const double per = p.th[0], l = p.th[1];
-        const double r = sqrt(acc);
-        const double sn = sin(PI_D * r / per);
-        const double k = exp(-2.0 * (sn * sn) / (l * l));     // GP_regression.py:49
-        if (WITH_DK) {
-            dk[0] = k * (2.0 * PI_D * r / (per * per * l * l)) * sin(2.0 * PI_D * r / per);
-            dk[1] = k * 4.0 * (sn * sn) / (l * l * l);
-        }
-        return k;
-    } else {  // CO2 composite, CO2_example.py:9-94
-        const double* t = p.th;
-        const double d = acc;
-        const double r = sqrt(d);
-        const double e1 = exp(-.5 * d / (t[1] * t[1]));                       // :17
-        const double sn = sin(PI_D * r);
-        const double q = sn / t[4];
-        const double e2 = exp(-.5 * d / (t[3] * t[3]) + -2.0 * (q * q));      // :30-32
-        const double u = 1.0 + .5 * d / (t[7] * (t[6] * t[6]));               // :44
-        const double pw = 1.0 / pow(u, t[7]);                                 // :45
-        const double e4 = exp(-.5 * d / (t[9] * t[9]));                       // :65
-        const double k1 = (t[0] * t[0]) * e1;
-        const double k2 = (t[2] * t[2]) * e2;
-        const double k3 = (t[5] * t[5]) * pw;
-        double k4 = (t[8] * t[8]) * e4;
-        if (diag) k4 += t[10] * t[10];                                        // :66 (delta iff square block)
-        if (WITH_DK) {
-            dk[0] = 2.0 * t[0] * e1;
-            dk[1] = k1 * d / (t[1] * t[1] * t[1]);
-            dk[2] = 2.0 * k2 / t[2];
-            dk[3] = k2 * d / (t[3] * t[3] * t[3]);
-            dk[4] = k2 * 4.0 * (sn * sn) / (t[4] * t[4] * t[4]);
-            dk[5] = 2.0 * k3 / t[5];
-            dk[6] = k3 * d / (t[6] * t[6] * t[6] * u);
-            dk[7] = k3 * (-log(u) + (u - 1.0) / u);
-            dk[8] = 2.0 * t[8] * e4;
-            dk[9] = (t[8] * t[8]) * e4 * d / (t[9] * t[9] * t[9]);
-            dk[10] = diag ? 2.0 * t[10] : 0.0;
-        }
-        return ((k1 + k2) + k3) + k4;                                         // :90-93 (left-to-right sum)
-    }
-}
 
 // Accumulate pairwise terms for a 128x128 tile: thread (tx = tid&31, ty = tid>>5) owns rows ty+16i (i<8)
 // and columns tx+32j (j<4).  xs1: [128][DCH] row tile, xs2: [DCH][128] transposed column tile.
@@ -169,7 +105,7 @@ __global__ void __launch_bounds__(CTHREADS) cov_build_kernel(CovParams p, const 
             double dk[11];
             double v;
             if (r < n1 && c < n2) {
-                const bool diag = same && (r == c);
+                const bool diag = (flags & (GPX_COV_SAME_X | GPX_COV_DELTA)) && (r == c);
                 double a = acc[i][j];
                 v = cov_eval<KIND, WITH_DK>(p, a, aux[i][j], diag, dk);
                 if (diag) v += diag_add;
@@ -316,7 +252,7 @@ extern "C" int gpx_cov_build(gpx_handle h, int kind, const double* X1, int64_t n
     GPX_REQUIRE(n1 > 0 && n2 > 0, 4);
     GPX_REQUIRE(n1p >= n1 && n1p % TM == 0 && n2p >= n2 && n2p % TN == 0, 13);
     GPX_REQUIRE(ldk >= n2p, 15);
-    GPX_REQUIRE(!(flags & GPX_COV_SAME_X) || (n1 == n2), 11);
+    GPX_REQUIRE(!(flags & (GPX_COV_SAME_X | GPX_COV_DELTA)) || (n1 == n2), 11);
     CovParams p;
     GPX_TRY(make_params(kind, D, theta_host, ntheta, &p));
     if (dK) return launch_build<true>(h, p, X1, n1, X2, n2, diag_add, flags, K, n1p, n2p, ldk, dK, dk_stride);

@@ -14,7 +14,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import COV_CO2, COV_LIN, COV_LOWER, COV_PER, COV_SAME_X, COV_SE, GPX_TILE, GpxError, check
+from ._lib import COV_CO2, COV_DELTA, COV_LIN, COV_LOWER, COV_PER, COV_SAME_X, COV_SE, GPX_TILE, GpxError, check
 
 _KIND_NTHETA = {COV_SE: 2, COV_LIN: 1, COV_PER: 2, COV_CO2: 11}
 
@@ -115,7 +115,7 @@ class Engine:
 
     # ------------------------------------------------------------------ A1-A3 covariance
     def cov(self, kind: int, X1, X2, theta, diag_add: float = 0.0, same_x: bool = False, lower: bool = False,
-            out=None, with_grad: bool = False):
+            out=None, with_grad: bool = False, delta: bool = False):
         """K (padded) = k(X1, X2; theta) [+ diag_add I].  Returns K or (K, dK[ntheta]) device tensors."""
         self._sync_stream()
         n1, D = X1.shape
@@ -123,7 +123,7 @@ class Engine:
         n1p, n2p = padded(n1), padded(n2)
         K = out if out is not None else self.empty(n1p, n2p)
         th, thp = _theta_array(theta)
-        flags = (COV_SAME_X if same_x else 0) | (COV_LOWER if lower else 0)
+        flags = (COV_SAME_X if same_x else 0) | (COV_LOWER if lower else 0) | (COV_DELTA if delta else 0)
         dK = self.empty(len(th), n1p, n2p) if with_grad else None
         check(self.lib.gpx_cov_build(self.h, kind, self._p(X1), n1, self._p(X2), n2, D, thp, len(th), float(diag_add), flags,
                                      self._p(K), n1p, n2p, K.stride(0), self._p(dK), n1p * n2p), "gpx_cov_build")
@@ -300,6 +300,67 @@ class Engine:
         fit.Kinv = self.lauum(fit.L, work)
         return fit.Kinv
 
+    # ------------------------------------------------------------------ fused small-problem posterior
+    def small_max(self) -> int:
+        return int(self.lib.gpx_small_max())
+
+    def small_posterior(self, kind: int, X, y, Xs, theta, s: float, jitter: float, Z=None):
+        """mu, var, f_post (or None), lml of GP_regression.py:109-156 in ONE kernel launch; host arrays in and out.
+
+        Requires N <= small_max(); with Z (the caller's standard normals, (n, num_fun)) also n <= small_max(),
+        without Z any number of test points (one thread block per small_max() of them)."""
+        self._sync_stream()
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        Xs = np.ascontiguousarray(Xs, dtype=np.float64)
+        y = np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1))
+        N, D = X.shape
+        n = Xs.shape[0]
+        th, thp = _theta_array(theta)
+        mu = np.empty(n)
+        var = np.empty(n)
+        lml = ctypes.c_double(0.0)
+        nf = 0
+        fpost = None
+        zp = fp = ctypes.c_void_p(0)
+        if Z is not None:
+            Z = np.ascontiguousarray(Z, dtype=np.float64)
+            nf = Z.shape[1]
+            fpost = np.empty((n, nf))
+            zp, fp = ctypes.c_void_p(Z.ctypes.data), ctypes.c_void_p(fpost.ctypes.data)
+        st = self.lib.gpx_gp_small_posterior_host(
+            self.h, kind, ctypes.c_void_p(X.ctypes.data), N, D, ctypes.c_void_p(y.ctypes.data),
+            ctypes.c_void_p(Xs.ctypes.data), n, thp, len(th), float(s), float(jitter), zp, nf,
+            ctypes.c_void_p(mu.ctypes.data), ctypes.c_void_p(var.ctypes.data), fp, ctypes.byref(lml))
+        check(st, "gpx_gp_small_posterior_host")
+        return mu, var, fpost, float(lml.value)
+
+    def small_fit(self, kind: int, X, y, Xs, theta, s: float, jitter: float):
+        """First half of the two-step small posterior: (mu, var, lml); the sampling factor stays on the device."""
+        self._sync_stream()
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        Xs = np.ascontiguousarray(Xs, dtype=np.float64)
+        y = np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1))
+        N, D = X.shape
+        n = Xs.shape[0]
+        th, thp = _theta_array(theta)
+        mu = np.empty(n)
+        var = np.empty(n)
+        lml = ctypes.c_double(0.0)
+        st = self.lib.gpx_gp_small_fit_host(
+            self.h, kind, ctypes.c_void_p(X.ctypes.data), N, D, ctypes.c_void_p(y.ctypes.data),
+            ctypes.c_void_p(Xs.ctypes.data), n, thp, len(th), float(s), float(jitter),
+            ctypes.c_void_p(mu.ctypes.data), ctypes.c_void_p(var.ctypes.data), ctypes.byref(lml))
+        check(st, "gpx_gp_small_fit_host")
+        return mu, var, float(lml.value)
+
+    def small_sample(self, n: int, Z) -> np.ndarray:
+        """Second half: mu + L_ Z for the factor kept by the last small_fit (Z: (n, num_fun) standard normals)."""
+        Z = np.ascontiguousarray(Z, dtype=np.float64)
+        fpost = np.empty(Z.shape)
+        check(self.lib.gpx_gp_small_sample_host(self.h, n, Z.shape[1], ctypes.c_void_p(Z.ctypes.data),
+                                                ctypes.c_void_p(fpost.ctypes.data)), "gpx_gp_small_sample_host")
+        return fpost
+
     # ------------------------------------------------------------------ A6 prediction
     def predict(self, fit: GPFit, Xs, want_v: bool = False, kss_diag=None):
         """mu = K_s^T alpha, var = diag(K_ss) - colsum((L^-1 K_s)^2)  (GP_regression.py:143-147).
@@ -310,7 +371,9 @@ class Engine:
             raise GpxError("predict() needs the factor L; this fit holds L^-1 (fit_grad overwrote it)")
         Xsd = self.to_device(Xs)
         m = Xsd.shape[0]
-        Ks = self.cov(fit.kind, fit.X, Xsd, fit.theta)                      # (npad, mpad)
+        # CO2_example.py:58-66 adds theta_11^2 * I to ANY square block, so also to K_s when N == n
+        square_co2 = fit.kind == COV_CO2 and fit.n == m
+        Ks = self.cov(fit.kind, fit.X, Xsd, fit.theta, delta=square_co2)    # (npad, mpad)
         mu = self.empty(m)
         var = self.empty(m)
         lib = self.lib

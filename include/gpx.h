@@ -52,6 +52,8 @@ enum gpx_cov_kind {
 /* flags for gpx_cov_build */
 #define GPX_COV_SAME_X   1   /* X1 is X2: square block; theta11^2 delta (CO2) and `diag_add` go on the diagonal */
 #define GPX_COV_LOWER    2   /* only tiles on/below the diagonal are computed; strictly-upper tiles are zeroed  */
+#define GPX_COV_DELTA    4   /* n1 == n2 but X1 is not X2 (a square CROSS block): the CO2 delta term still goes on
+                                the diagonal (CO2_example.py:58-66 tests the shape only); padding stays zero        */
 
 /* ---- library / handle ------------------------------------------------------------------- */
 int         gpx_version(void);
@@ -217,6 +219,25 @@ int gpx_potrf_mg(gpx_handle h, double* Aloc, int64_t n, int64_t ldl, int64_t nb,
 /* LML (+ optional gradient wrt all theta when grad_host != NULL) of y ~ GP(0, cov + s I). */
 int gpx_host_lml(gpx_handle h, int kind, const double* X, int64_t n, int D, const double* theta, int ntheta,
                  double s, const double* y, double* lml_out, double* grad_host);
+/* Whole posterior of GP_regression.py:109-156 (== tune...:67-101, CO2...:182-214) for SMALL problems in ONE kernel
+ * launch: requires N <= gpx_small_max() training points, and n <= gpx_small_max() test points when sampling (nf > 0;
+ * without sampling any n: one thread block per gpx_small_max() test points).  HOST pointers: X[N,D], y[N],
+ * Xs[n,D], Z[n,nf] (the caller's standard normals, drawn on the host so the NumPy RNG stream stays the reference's;
+ * nf = 0 skips sampling) -> mu[n], var[n] (NOT square-rooted; may be negative exactly where the reference yields NaN),
+ * fpost[n,nf] = mu + chol(K** + jitter I - V^T V) Z, lml.  Returns > 0 when K + s I (GP_regression.py:138) or the
+ * posterior covariance (:154) is not positive definite (index of the failing pivot). */
+int gpx_gp_small_posterior_host(gpx_handle h, int kind, const double* X, int64_t N, int D, const double* y,
+                                const double* Xs, int64_t n, const double* theta, int ntheta, double s, double jitter,
+                                const double* Z, int nf, double* mu, double* var, double* fpost, double* lml);
+int gpx_small_max(void);
+/* The same posterior in two steps, for hosts that must draw their normals AFTER the linear algebra succeeded (the
+ * reference raises LinAlgError at GP_regression.py:138/:154 before it consumes the RNG at :155):
+ * gpx_gp_small_fit_host -> mu, var, lml and keeps chol(K** + jitter I - V^T V) on the device (n <= gpx_small_max());
+ * gpx_gp_small_sample_host -> fpost[n,nf] = mu + L_ Z for the factor of the last successful fit on this handle. */
+int gpx_gp_small_fit_host(gpx_handle h, int kind, const double* X, int64_t N, int D, const double* y, const double* Xs,
+                          int64_t n, const double* theta, int ntheta, double s, double jitter, double* mu, double* var,
+                          double* lml);
+int gpx_gp_small_sample_host(gpx_handle h, int64_t n, int nf, const double* Z, double* fpost);
 
 #ifdef __cplusplus
 }

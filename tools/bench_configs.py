@@ -64,12 +64,22 @@ def main():
         from gaussian_process_b200 import GP_regression as G
         X, y, Xs = O.synth_c1(5, 100)
         np.random.seed(0)
-        tg, (mu, sd, fp) = gpu_time(lambda: G.prediction(X, Xs, y, 'rbf', 1, 10), reps=5)
+        G.FUSED_SMALL_PATH = False
+        tg_tiled, _ = gpu_time(lambda: G.prediction(X, Xs, y, 'rbf', 1, 10), reps=20, warm=3)
+        G.FUSED_SMALL_PATH = True
         np.random.seed(0)
-        tc, (mu_o, sd_o, _) = cpu_time(lambda: O.regression_prediction(X, Xs, y, 'rbf', 1, 10), reps=5)
-        print(json.dumps({"config": "C1 GP_regression.prediction N=5 n=100 D=1 (as shipped)", "gpu_s": tg, "cpu_s": tc, "cpu_cores": cores,
-                          "parity": {"mu": rel(mu, mu_o), "var": rel(sd ** 2, sd_o ** 2)},
-                          "note": "launch-latency bound: ~%d kernel launches for a 128-padded problem" % 60}))
+        tg, (mu, sd, fp) = gpu_time(lambda: G.prediction(X, Xs, y, 'rbf', 1, 10), reps=50, warm=3)
+        np.random.seed(0)
+        mu, sd, fp = G.prediction(X, Xs, y, 'rbf', 1, 10)
+        np.random.seed(0)
+        tc, _ = cpu_time(lambda: O.regression_prediction(X, Xs, y, 'rbf', 1, 10), reps=50)
+        np.random.seed(0)
+        mu_o, sd_o, fp_o = O.regression_prediction(X, Xs, y, 'rbf', 1, 10)
+        print(json.dumps({"config": "C1 GP_regression.prediction N=5 n=100 D=1 (as shipped)", "gpu_s": tg, "gpu_s_tiled_path": tg_tiled,
+                          "cpu_s": tc, "cpu_cores": cores,
+                          "parity": {"mu": rel(mu, mu_o), "var": rel(sd ** 2, sd_o ** 2), "f_post": rel(fp, fp_o)},
+                          "note": "fused path: one H2D copy, ONE kernel launch (csrc/small.cu), one D2H copy; tiled path: ~60 launches "
+                                  "and 6 host synchronisations for a 128-padded problem"}))
 
     if "c2" in want:
         from gaussian_process_b200 import CO2_example as C2
