@@ -44,6 +44,8 @@ def covariance_function(a, b, hyperparms):
 def compute_mar_likelihood(X_train, y_train, hyperparms):
     """log p(y | X, theta), s = 5e-4 (CO2...:131-149)."""
     eng = get_engine()
+    if _gpr.FUSED_SMALL_PATH and len(X_train) <= eng.small_max():
+        return np.float64(eng.small_lml_grad(COV_CO2, X_train, y_train, _theta(hyperparms), NOISE_VARIANCE, with_grad=False)[0])
     fit = eng.fit(COV_CO2, np.asarray(X_train, dtype=np.float64), y_train, _theta(hyperparms), NOISE_VARIANCE)
     return np.float64(fit.lml)
 
@@ -51,6 +53,9 @@ def compute_mar_likelihood(X_train, y_train, hyperparms):
 def compute_mar_likelihood_gradient(X_train, y_train, hyperparms):
     """(LML, dLML/dtheta[11]) -- the multi-theta generalisation of tune...:31-64."""
     eng = get_engine()
+    if _gpr.FUSED_SMALL_PATH and len(X_train) <= eng.small_max():
+        lml, grad = eng.small_lml_grad(COV_CO2, X_train, y_train, _theta(hyperparms), NOISE_VARIANCE)
+        return np.float64(lml), grad
     fit = eng.fit(COV_CO2, np.asarray(X_train, dtype=np.float64), y_train, _theta(hyperparms), NOISE_VARIANCE, with_grad=True)
     return np.float64(fit.lml), fit.grad
 

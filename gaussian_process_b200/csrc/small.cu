@@ -50,6 +50,23 @@ __device__ __noinline__ double pair_value(const CovParams& p, const double* __re
     return cov_eval<KIND, false>(p, acc, aux, diag, dk);
 }
 
+// The same entry together with d/dtheta_q for every hyper-parameter (dk: NTheta<KIND> doubles).
+template <int KIND>
+__device__ __noinline__ double pair_value_dk(const CovParams& p, const double* __restrict__ a,
+                                             const double* __restrict__ b, bool diag, double* dk) {
+    double acc = 0.0, aux = 0.0;
+    for (int d = 0; d < p.D; ++d) {
+        if (KIND == GPX_COV_LIN) {
+            acc += (a[d] - p.th[0]) * (b[d] - p.th[0]);
+            aux += a[d] + b[d];
+        } else {
+            const double df = a[d] - b[d];
+            acc += df * df;
+        }
+    }
+    return cov_eval<KIND, true>(p, acc, aux, diag, dk);
+}
+
 // In-place Cholesky of a packed lower triangle in shared memory.  rdiag / rinv receive L_kk and 1 / L_kk; pinv is
 // scratch for the pivot reciprocals.  Returns 0, or the 1-based index of the first non-positive pivot (uniform
 // over the block).  A column step is bound by instruction issue (every warp walks the step's control code), so
@@ -266,6 +283,132 @@ __global__ void __launch_bounds__(ST) gp_small_sample_kernel(int n, int nf, cons
     }
 }
 
+// LML and dLML/dtheta for N <= 128 in one block, optionally the reference's whole gradient-ascent loop on the SE
+// length-scale (tune_hyperparms_regression.py:121-153) without leaving the kernel:
+//   K + s I -> L;  [L^-1 | m] = L^-1 [I | y];  alpha = L^-T m;  LML (tune...:141);
+//   grad_q = 1/2 sum_ij (alpha_i alpha_j - (L^-T L^-1)_ij) dK_ij/dtheta_q            (tune...:55-57,144)
+//   ascent: l <- l + step * grad_l, stop once |LML - LML_old| <= tol (the step is still taken), at most max_iter.
+// in : [X N*D][y N]     out : [lml, info, iters, l_final, l_used, error, converged, 0, grad[11]]
+template <int KIND>
+__global__ void __launch_bounds__(ST, 1) gp_small_grad_kernel(const __grid_constant__ CovParams p0, int N, double s,
+                                                              int want_grad, int ascent, double step, double tol,
+                                                              int max_iter, const double* __restrict__ in,
+                                                              double* __restrict__ out) {
+    extern __shared__ double sm[];
+    constexpr int NT = NTheta<KIND>::value;
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const int D = p0.D;
+    const int nv = N + 1;
+    const double* X = in;
+    const double* y = X + (size_t)N * D;
+    double* Lp = sm;                               // packed K + s I -> L
+    double* Vs = Lp + N * (N + 1) / 2;             // N x nv: [I | y] -> [L^-1 | m]
+    double* al = Vs + N * nv;                      // alpha
+    double* rdiag = al + N;
+    double* rinv = rdiag + N;
+    double* pinv = rinv + N;
+    double* red = pinv + (N < 12 ? 12 : N);        // 32 warps x (NT + 1) partial sums; the totals land in pinv[0..NT]
+
+    CovParams p = p0;
+    double lml_old = 0.0, lml = 0.0, err = 0.0, l_used = p.th[1];
+    int it = 0, converged = 0;
+    for (;;) {
+#pragma unroll 1
+        for (int ab = 0; ab < 16; ++ab) {
+            const int i = ty + 32 * (ab >> 2), j = tx + 32 * (ab & 3);
+            if (i < N && j <= i) {
+                double v = pair_value<KIND>(p, X + (size_t)i * D, X + (size_t)j * D, i == j);
+                if (i == j) v += s;
+                Lp[tri(i, j)] = v;
+            }
+        }
+#pragma unroll 1
+        for (int i = ty; i < N; i += 32) {
+            for (int c = tx; c < N; c += 32) Vs[i * nv + c] = (c == i) ? 1.0 : 0.0;
+            if (tx == 0) Vs[i * nv + N] = y[i];
+        }
+        const int info = chol_packed(Lp, N, rdiag, rinv, pinv);
+        if (info) {
+            if (tid == 0) { out[0] = 0.0; out[1] = info; out[2] = it; }
+            return;
+        }
+        for (int k = 0; k < N; ++k) {              // [L^-1 | m]: one barrier per step, row k scaled at the end
+            __syncthreads();
+            const double rk = rinv[k];
+#pragma unroll 1
+            for (int i = k + 1 + ty; i < N; i += ST / 32) {
+                const double lik = Lp[tri(i, k)] * rk;
+                for (int c = tx; c < nv; c += 32)
+                    if (c <= k || c == N) Vs[i * nv + c] -= lik * Vs[k * nv + c];   // columns > k of row k are zero
+            }
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int i = ty; i < N; i += ST / 32)
+            for (int c = tx; c < nv; c += 32) Vs[i * nv + c] *= rinv[i];
+        __syncthreads();
+        for (int j = tid; j < N; j += ST) {        // alpha = L^-T m
+            double a = 0.0;
+            for (int r = j; r < N; ++r) a += Vs[r * nv + j] * Vs[r * nv + N];
+            al[j] = a;
+        }
+        double part[NT + 1];
+#pragma unroll
+        for (int q = 0; q <= NT; ++q) part[q] = 0.0;
+        if (ty == 31) {                            // last warp: the two LML sums, folded into slot NT
+            for (int i = tx; i < N; i += 32) {
+                const double m = Vs[i * nv + N];
+                part[NT] += -.5 * m * m - log(rdiag[i]);
+            }
+        }
+        __syncthreads();
+        if (want_grad) {
+#pragma unroll 1
+            for (int ab = 0; ab < 16; ++ab) {
+                const int i = ty + 32 * (ab >> 2), j = tx + 32 * (ab & 3);
+                if (i < N && j <= i) {
+                    double kinv = 0.0;
+                    for (int r = i; r < N; ++r) kinv += Vs[r * nv + i] * Vs[r * nv + j];
+                    double dk[NT];
+                    pair_value_dk<KIND>(p, X + (size_t)i * D, X + (size_t)j * D, i == j, dk);
+                    const double wgt = (al[i] * al[j] - kinv) * (i == j ? .5 : 1.0);
+#pragma unroll
+                    for (int q = 0; q < NT; ++q) part[q] += wgt * dk[q];
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q <= NT; ++q) {
+            double v = part[q];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (tx == 0) red[ty * (NT + 1) + q] = v;
+        }
+        __syncthreads();
+        if (tid <= NT) {
+            double v = 0.0;
+            for (int w = 0; w < ST / 32; ++w) v += red[w * (NT + 1) + tid];
+            pinv[tid] = v;                         // pinv is free between factorisations (sized >= 12 by the host)
+        }
+        __syncthreads();
+        lml = pinv[NT] - N / 2.0 * log(2.0 * PI_D);
+        ++it;
+        if (!ascent) break;
+        err = fabs(lml - lml_old);                 // tune...:130
+        l_used = p.th[1];
+        p.th[1] += step * pinv[1];                 // tune...:63 (sigma's update is commented out in the reference)
+        lml_old = lml;
+        if (err <= tol) { converged = 1; break; }
+        if (it >= max_iter) break;
+        __syncthreads();                           // pinv / red are rewritten by the next iteration
+    }
+    if (tid == 0) {
+        out[0] = lml; out[1] = 0.0; out[2] = it; out[3] = p.th[1]; out[4] = l_used; out[5] = err; out[6] = converged;
+        out[7] = 0.0;
+    }
+    if (tid < NT) out[8 + tid] = pinv[tid];
+}
+
 int ensure_pinned(gpx_ctx* h, size_t bytes) {
     if (h->pinned_bytes >= bytes) return 0;
     if (h->pinned) {
@@ -395,5 +538,93 @@ extern "C" int gpx_gp_small_sample_host(gpx_handle h, int64_t n, int nf, const d
     GPX_CUDA(cudaMemcpyAsync(hz + nZ, dz + nZ, nZ * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     GPX_CUDA(cudaStreamSynchronize(h->stream));
     memcpy(fpost, hz + nZ, nZ * sizeof(double));
+    return 0;
+}
+
+namespace {
+
+template <int KIND>
+int launch_small_grad(gpx_ctx* h, const CovParams& p, int N, double s, int want_grad, int ascent, double step, double tol,
+                      int max_iter, const double* in, double* out, size_t smem) {
+    static bool configured = false;
+    if (!configured) {
+        GPX_CUDA(cudaFuncSetAttribute(gp_small_grad_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    gp_small_grad_kernel<KIND><<<1, ST, smem, h->stream>>>(p, N, s, want_grad, ascent, step, tol, max_iter, in, out);
+    GPX_CHECK_LAUNCH(h);
+    return 0;
+}
+
+int small_grad_run(gpx_ctx* h, int kind, const double* X, int64_t N, int D, const double* y, const double* theta, int ntheta,
+                   double s, int want_grad, int ascent, double step, double tol, int max_iter, double* out19) {
+    GPX_REQUIRE(h != nullptr, 1);
+    GPX_REQUIRE(kind >= 0 && kind <= 3, 2);
+    GPX_REQUIRE(N >= 1 && N <= SMAX, 4);
+    GPX_REQUIRE(D >= 1, 5);
+    GPX_REQUIRE(X && y && theta && out19, 3);
+    CovParams p;
+    {
+        static const int expect[4] = {2, 1, 2, 11};
+        GPX_REQUIRE(expect[kind] == ntheta, 8);
+        p.kind = kind;
+        p.ntheta = ntheta;
+        p.D = D;
+        for (int i = 0; i < 11; ++i) p.th[i] = i < ntheta ? theta[i] : 0.0;
+    }
+    const size_t nX = (size_t)N * D, in_elems = nX + N, out_elems = 19;
+    const size_t pv = N < 12 ? 12 : N;               // pinv doubles as the 12-slot reduction result
+    const size_t smem = ((size_t)N * (N + 1) / 2 + (size_t)N * (N + 1) + 3 * N + pv + 32 * 12) * sizeof(double);
+    GPX_REQUIRE(smem <= 227 * 1024, 4);
+    GPX_TRY(ensure_pinned(h, (in_elems + out_elems) * sizeof(double)));
+    void* dev = nullptr;
+    GPX_TRY(gpx_scratch(h, (in_elems + out_elems) * sizeof(double), &dev));
+    double* hin = (double*)h->pinned;
+    double* hout = hin + in_elems;
+    double* din = (double*)dev;
+    double* dout = din + in_elems;
+    memcpy(hin, X, nX * sizeof(double));
+    memcpy(hin + nX, y, (size_t)N * sizeof(double));
+    GPX_CUDA(cudaMemcpyAsync(din, hin, in_elems * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    int r;
+    switch (kind) {
+        case GPX_COV_SE: r = launch_small_grad<GPX_COV_SE>(h, p, (int)N, s, want_grad, ascent, step, tol, max_iter, din, dout, smem); break;
+        case GPX_COV_LIN: r = launch_small_grad<GPX_COV_LIN>(h, p, (int)N, s, want_grad, ascent, step, tol, max_iter, din, dout, smem); break;
+        case GPX_COV_PER: r = launch_small_grad<GPX_COV_PER>(h, p, (int)N, s, want_grad, ascent, step, tol, max_iter, din, dout, smem); break;
+        default: r = launch_small_grad<GPX_COV_CO2>(h, p, (int)N, s, want_grad, ascent, step, tol, max_iter, din, dout, smem); break;
+    }
+    if (r != 0) return r;
+    GPX_CUDA(cudaMemcpyAsync(hout, dout, out_elems * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    GPX_CUDA(cudaStreamSynchronize(h->stream));
+    memcpy(out19, hout, out_elems * sizeof(double));
+    if (hout[1] != 0.0) return (int)hout[1];         // K + s I not positive definite (tune...:127)
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int gpx_gp_small_lml_grad_host(gpx_handle h, int kind, const double* X, int64_t N, int D, const double* y,
+                                          const double* theta, int ntheta, double s, double* lml, double* grad) {
+    GPX_REQUIRE(lml != nullptr, 10);
+    double out[19];
+    GPX_TRY(small_grad_run(h, kind, X, N, D, y, theta, ntheta, s, grad != nullptr, 0, 0.0, 0.0, 1, out));
+    *lml = out[0];
+    if (grad)
+        for (int q = 0; q < ntheta; ++q) grad[q] = out[8 + q];
+    return 0;
+}
+
+extern "C" int gpx_gp_small_ascent_host(gpx_handle h, const double* X, int64_t N, int D, const double* y, double sigma,
+                                        double l0, double s, double step, double tol, int max_iter, double* out6) {
+    GPX_REQUIRE(out6 != nullptr && max_iter >= 1, 11);
+    const double theta[2] = {sigma, l0};
+    double out[19];
+    GPX_TRY(small_grad_run(h, GPX_COV_SE, X, N, D, y, theta, 2, s, 1, 1, step, tol, max_iter, out));
+    out6[0] = out[2];   // iterations done
+    out6[1] = out[3];   // l after the last step
+    out6[2] = out[4];   // l the last iteration was evaluated at
+    out6[3] = out[0];   // LML of the last iteration
+    out6[4] = out[5];   // |LML - LML_old| of the last iteration
+    out6[5] = out[6];   // 1 when the tolerance was met
     return 0;
 }

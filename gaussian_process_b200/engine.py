@@ -361,6 +361,33 @@ class Engine:
                                                 ctypes.c_void_p(fpost.ctypes.data)), "gpx_gp_small_sample_host")
         return fpost
 
+    def small_lml_grad(self, kind: int, X, y, theta, s: float, with_grad: bool = True):
+        """(lml, grad or None) for N <= small_max() in one kernel launch (host arrays in, host scalars out)."""
+        self._sync_stream()
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        y = np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1))
+        th, thp = _theta_array(theta)
+        lml = ctypes.c_double(0.0)
+        grad = np.empty(len(th)) if with_grad else None
+        st = self.lib.gpx_gp_small_lml_grad_host(
+            self.h, kind, ctypes.c_void_p(X.ctypes.data), X.shape[0], X.shape[1], ctypes.c_void_p(y.ctypes.data), thp,
+            len(th), float(s), ctypes.byref(lml), ctypes.c_void_p(grad.ctypes.data) if with_grad else None)
+        check(st, "gpx_gp_small_lml_grad_host")
+        return float(lml.value), grad
+
+    def small_ascent(self, X, y, sigma: float, l0: float, s: float, step: float, tol: float, max_iter: int):
+        """tune_hyperparms_regression.py:121-153 in one launch -> dict(iterations, l, l_used, lml, error, converged)."""
+        self._sync_stream()
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        y = np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1))
+        out = np.empty(6)
+        st = self.lib.gpx_gp_small_ascent_host(
+            self.h, ctypes.c_void_p(X.ctypes.data), X.shape[0], X.shape[1], ctypes.c_void_p(y.ctypes.data), float(sigma),
+            float(l0), float(s), float(step), float(tol), int(max_iter), ctypes.c_void_p(out.ctypes.data))
+        check(st, "gpx_gp_small_ascent_host")
+        return dict(iterations=int(out[0]), l=float(out[1]), l_used=float(out[2]), lml=float(out[3]), error=float(out[4]),
+                    converged=bool(out[5]))
+
     # ------------------------------------------------------------------ A6 prediction
     def predict(self, fit: GPFit, Xs, want_v: bool = False, kss_diag=None):
         """mu = K_s^T alpha, var = diag(K_ss) - colsum((L^-1 K_s)^2)  (GP_regression.py:143-147).

@@ -85,6 +85,8 @@ def tune_hyperparms_first(X_train, X_test, y_train, num_fun, sigma, l):
     eng = get_engine()
     X_train = np.asarray(X_train, dtype=np.float64)
     X_test = np.asarray(X_test, dtype=np.float64)
+    if _gpr.FUSED_SMALL_PATH and num_fun >= 1 and X_train.shape[0] <= eng.small_max() and X_test.shape[0] <= eng.small_max():
+        return _tune_first_small(eng, X_train, X_test, y_train, num_fun, sigma, l)
     Xd = eng.to_device(X_train)
     yd = eng.to_device(np.asarray(y_train, dtype=np.float64).reshape(-1))
     Xs = eng.to_device(X_test)
@@ -122,10 +124,33 @@ def tune_hyperparms_first(X_train, X_test, y_train, num_fun, sigma, l):
     return mu_post, stand_devi, f_post_fun, optimal_likelihood
 
 
+def _tune_first_small(eng, X_train, X_test, y_train, num_fun, sigma, l):
+    """As-shipped sizes (N <= 128): the whole ascent loop is ONE kernel launch with all state in shared memory
+    (csrc/small.cu, gp_small_grad_kernel), then the one-launch posterior at the length-scale of the last iteration."""
+    sig = float(np.asarray(sigma).reshape(-1)[0])
+    res = eng.small_ascent(X_train, y_train, sig, float(np.asarray(l).reshape(-1)[0]), NOISE_VARIANCE, STEP_SIZE,
+                           TOLERANCE, 10000)
+    l = np.full(np.shape(l), res["l"]) if isinstance(l, np.ndarray) else res["l"]
+    if res["converged"]:
+        print("The hyperparameter tuning function has already converged after " + repr(res["iterations"]) + " iterations!")
+        print("The error is " + _r(res["error"]))
+        print("training end!")
+    optimal_likelihood = np.float64(res["lml"])
+    print('optimal lenghscalar is: ' + _r(l))
+    print('maximum log marginal likelihood is: ' + _r(optimal_likelihood))
+    mu_post, var, _ = eng.small_fit(COV_SE, X_train, y_train, X_test, [sig, res["l_used"]], NOISE_VARIANCE, 1e-6)
+    with np.errstate(invalid="ignore"):
+        stand_devi = np.sqrt(var)
+    z = np.random.normal(size=(X_test.shape[0], num_fun))                   # tune...:160
+    return mu_post, stand_devi, eng.small_sample(X_test.shape[0], z), optimal_likelihood
+
+
 def compute_mar_likelihood(X_train, X_test, y_train, sigma, l):
     """log p(y | X, sigma, l) with s = 5e-4.  tune_hyperparms_regression.py:292-313 (X_test unused)."""
     eng = get_engine()
     theta = [float(np.asarray(sigma).reshape(-1)[0]), float(np.asarray(l).reshape(-1)[0])]
+    if _gpr.FUSED_SMALL_PATH and len(X_train) <= eng.small_max():
+        return np.float64(eng.small_lml_grad(COV_SE, X_train, y_train, theta, NOISE_VARIANCE, with_grad=False)[0])
     fit = eng.fit(COV_SE, np.asarray(X_train, dtype=np.float64), y_train, theta, NOISE_VARIANCE)
     return np.float64(fit.lml)
 

@@ -238,6 +238,16 @@ int gpx_gp_small_fit_host(gpx_handle h, int kind, const double* X, int64_t N, in
                           int64_t n, const double* theta, int ntheta, double s, double jitter, double* mu, double* var,
                           double* lml);
 int gpx_gp_small_sample_host(gpx_handle h, int64_t n, int nf, const double* Z, double* fpost);
+/* LML (tune...:292-313, CO2...:131-149) and, when grad != NULL, dLML/dtheta for every hyper-parameter
+ * (tune...:31-64,144 generalised per SURVEY Appendix C) for N <= gpx_small_max() in one kernel launch. */
+int gpx_gp_small_lml_grad_host(gpx_handle h, int kind, const double* X, int64_t N, int D, const double* y,
+                               const double* theta, int ntheta, double s, double* lml, double* grad);
+/* The reference's whole gradient-ascent loop on the SE length-scale (tune_hyperparms_regression.py:121-153) inside ONE
+ * kernel launch, all state in shared memory: l <- l + step * dLML/dl until |LML - LML_old| <= tol (LML_old starts at 0;
+ * the step of the converging iteration is still taken) or max_iter iterations.  out6 = [iterations, l after the last
+ * step, l the last iteration was evaluated at, its LML, its |LML - LML_old|, converged flag]. */
+int gpx_gp_small_ascent_host(gpx_handle h, const double* X, int64_t N, int D, const double* y, double sigma, double l0,
+                             double s, double step, double tol, int max_iter, double* out6);
 
 #ifdef __cplusplus
 }

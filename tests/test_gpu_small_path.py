@@ -157,3 +157,83 @@ def test_fused_not_positive_definite_raises_and_restores_rng(G):
         assert np.array_equal(now[1], st[1]) and now[2:] == st[2:]
     finally:
         G.NOISE_VARIANCE = old_s
+
+
+# ------------------------------------------------------------------ fused LML / gradient / ascent loop (N <= 128)
+@pytest.mark.parametrize("fused", [True, False])
+def test_tune_first_loop_both_paths(G, golden, fused):
+    """tune_hyperparms_first at N=8: same iteration count, moments and LML as the unmodified reference, whether the
+    ascent loop runs inside one kernel (fused) or as one fused fit+grad call per iteration (tiled)."""
+    import contextlib
+    import io
+    from gaussian_process_b200 import tune_hyperparms_regression as T
+    G.FUSED_SMALL_PATH = fused
+    g = golden("ka2_tune_first.npz")
+    X, y, Xs = O.synth_c1(8, 100)
+    np.random.seed(3)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        mu, sd, fp, lml = T.tune_hyperparms_first(X, Xs, y, 2, 1, np.array([1.7]))
+    ref_txt = str(g["stdout"])
+    assert buf.getvalue().splitlines()[0] == ref_txt.splitlines()[0]          # same iteration count
+    assert rel(mu, g["mu"]) < 1e-7 and rel(sd ** 2, g["sd"] ** 2) < 1e-6 and rel(lml, g["lml"]) < TOL
+    assert fp.shape == (100, 2)
+
+
+def test_small_ascent_matches_oracle_loop():
+    from gaussian_process_b200 import get_engine
+    eng = get_engine()
+    X, y, Xs = O.synth_c1(12, 20)
+    np.random.seed(0)
+    mu_o, sd_o, fp_o, lml_o, l_o, it_o = O.tune_first(X, Xs, y, 1, 1.0, np.array([0.6]))
+    res = eng.small_ascent(X, y, 1.0, 0.6, 5e-4, 0.01, 1e-3, 10000)
+    assert res["iterations"] == it_o and res["converged"]
+    assert rel(res["l"], l_o) < 1e-8 and rel(res["lml"], lml_o) < TOL
+    capped = eng.small_ascent(X, y, 1.0, 0.6, 5e-4, 0.01, 0.0, 7)
+    assert capped["iterations"] == 7 and not capped["converged"]
+
+
+@pytest.mark.parametrize("N,D", [(1, 1), (100, 3), (128, 16)])
+def test_small_lml_grad_se_vs_oracle(N, D):
+    from gaussian_process_b200 import get_engine
+    from gaussian_process_b200._lib import COV_SE
+    eng = get_engine()
+    rs = np.random.RandomState(N)
+    X = rs.randn(N, D)
+    y = np.sin(X.sum(1)) + 0.05 * rs.randn(N)
+    lml, grad = eng.small_lml_grad(COV_SE, X, y, [1.3, 2.1], 5e-4)
+    K = O.rbf_kernel(X, X, 1.3, 2.1) + 5e-4 * np.eye(N)
+    L = np.linalg.cholesky(K)
+    alpha = np.linalg.solve(L.T, np.linalg.solve(L, y))
+    Kinv = np.dot(np.linalg.inv(L.T), np.linalg.inv(L))
+    assert rel(lml, O.lml_from(L, y, alpha)) < TOL
+    ref = O.lml_grad_from(alpha, Kinv, O.rbf_dcov(X, 1.3, 2.1))
+    assert np.all(np.abs(grad - ref) <= 1e-7 * np.maximum(1.0, np.abs(ref))), (grad, ref)
+    # the reference's own GEMM + trace form for dLML/dl (tune...:54-57)
+    assert abs(grad[1] - O.rbf_grad_l(X, 1.3, 2.1, alpha, Kinv)) <= 1e-7 * max(1.0, abs(grad[1]))
+    lml_only, none = eng.small_lml_grad(COV_SE, X, y, [1.3, 2.1], 5e-4, with_grad=False)
+    assert none is None and lml_only == lml
+
+
+def test_small_co2_lml_and_gradient_both_paths(G):
+    from gaussian_process_b200 import CO2_example as C2
+    X, y, _ = O.synth_c2(120)
+    th = O.CO2_THETA_BOOK
+    K = O.co2_covariance(X, X, th) + O.S_NOISE * np.eye(120)
+    Kinv = np.linalg.inv(K)
+    ref = O.lml_grad_from(Kinv @ y, Kinv, O.co2_dcov(X, th))
+    lml_o = O.co2_lml(X, y, th)
+    for fused in (True, False):
+        G.FUSED_SMALL_PATH = fused
+        assert rel(C2.compute_mar_likelihood(X, y, th), lml_o) < TOL, fused
+        lml, grad = C2.compute_mar_likelihood_gradient(X, y, th)
+        assert rel(lml, lml_o) < TOL, fused
+        assert np.all(np.abs(grad - ref) <= 1e-6 * np.maximum(1.0, np.abs(ref))), (fused, grad, ref)
+
+
+def test_small_lml_not_positive_definite_raises():
+    from gaussian_process_b200 import get_engine
+    from gaussian_process_b200._lib import COV_SE
+    X, y, _ = O.synth_c1(10, 5)
+    with pytest.raises(np.linalg.LinAlgError):
+        get_engine().small_lml_grad(COV_SE, X, y, [1.0, 1.0], -3.0)

@@ -53,7 +53,7 @@ def quiet(fn, *a, **k):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="c1,c2,c3,c4")
+    ap.add_argument("--configs", default="c1,n1,c2,c3,c4")
     ap.add_argument("--cpu-n", type=int, default=2048)
     a = ap.parse_args()
     eng = get_engine()
@@ -80,6 +80,24 @@ def main():
                           "parity": {"mu": rel(mu, mu_o), "var": rel(sd ** 2, sd_o ** 2), "f_post": rel(fp, fp_o)},
                           "note": "fused path: one H2D copy, ONE kernel launch (csrc/small.cu), one D2H copy; tiled path: ~60 launches "
                                   "and 6 host synchronisations for a 128-padded problem"}))
+
+    if "n1" in want:
+        # the gradient-ascent driver at an as-shipped size (N=12 train, n=100 test, 33 iterations)
+        from gaussian_process_b200 import GP_regression as G
+        from gaussian_process_b200 import tune_hyperparms_regression as T
+        X, y, Xs = O.synth_c1(12, 100)
+        out = {}
+        for name, fused in (("gpu_s_tiled_path", False), ("gpu_s", True)):
+            G.FUSED_SMALL_PATH = fused
+            np.random.seed(0)
+            out[name], res = gpu_time(lambda: quiet(T.tune_hyperparms_first, X, Xs, y, 1, 1.0, np.array([0.6])), reps=5 if fused else 2)
+        np.random.seed(0)
+        tc, ref = cpu_time(lambda: O.tune_first(X, Xs, y, 1, 1.0, np.array([0.6])), reps=5)
+        print(json.dumps({"config": "N1 tune_hyperparms_first N=12 n=100 (gradient ascent on l, %d iterations)" % ref[5], **out,
+                          "cpu_s": tc, "cpu_cores": cores,
+                          "parity": {"lml": rel(res[3], ref[3]), "mu": rel(res[0], ref[0])},
+                          "note": "fused path: the whole ascent loop is ONE kernel launch (gp_small_grad_kernel, all state in shared "
+                                  "memory) + the one-launch posterior; tiled path: one fused fit+grad call (~100 launches) per iteration"}))
 
     if "c2" in want:
         from gaussian_process_b200 import CO2_example as C2
