@@ -53,7 +53,7 @@ def quiet(fn, *a, **k):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="c1,n1,c2,c3,c4")
+    ap.add_argument("--configs", default="c1,n1,a10,a11,c2,c3,c4")
     ap.add_argument("--cpu-n", type=int, default=2048)
     a = ap.parse_args()
     eng = get_engine()
@@ -98,6 +98,29 @@ def main():
                           "parity": {"lml": rel(res[3], ref[3]), "mu": rel(res[0], ref[0])},
                           "note": "fused path: the whole ascent loop is ONE kernel launch (gp_small_grad_kernel, all state in shared "
                                   "memory) + the one-launch posterior; tiled path: one fused fit+grad call (~100 launches) per iteration"}))
+
+    if "a10" in want:
+        # binary Laplace at the as-shipped size (KA4: N=128, reference-faithful mode, 138 iterations)
+        from gaussian_process_b200 import GP_binary_classification as B
+        g = np.load(os.path.join(ROOT, "tests", "golden", "ka4_binary.npz"))
+        X, y, fpr = g["X"], g["y"], g["f_prior"]
+        K = O.rbf_kernel(X, X, 1, 1)
+        tg, (W, L_inv, fd) = gpu_time(lambda: quiet(B.model_training, K, y, fpr, 1), reps=3)
+        tc, ref = cpu_time(lambda: quiet(O.binary_training_reference, K, y, fpr, 1), reps=3)
+        print(json.dumps({"config": "A10 GP_binary_classification.model_training N=128 (as shipped, reference-faithful, 138 iterations)",
+                          "gpu_s": tg, "cpu_s": tc, "cpu_cores": cores, "parity": {"L_inv": rel(L_inv, g["L_inv"]), "first_deri": rel(fd, g["first_deri"])}}))
+
+    if "a11" in want:
+        # multiclass Laplace at the as-shipped size (KA5: C=3, n=60, reference-faithful mode, 18 iterations)
+        from scipy.linalg import block_diag
+        from gaussian_process_b200 import GP_multi_classification as M
+        g = np.load(os.path.join(ROOT, "tests", "golden", "ka5_multi.npz"))
+        Ks = O.rbf_kernel(g["Xtr"], g["Xtr"], 1, 1)
+        Kb = block_diag(Ks, Ks, Ks)
+        tg, pi = gpu_time(lambda: quiet(M.model_training2, Kb, g["y_targets"], 3, 60), reps=3)
+        tc, ref = cpu_time(lambda: quiet(O.multi_training_reference, Kb, g["y_targets"], 3, 60), reps=3)
+        print(json.dumps({"config": "A11 GP_multi_classification.model_training2 C=3 n=60 (as shipped, reference-faithful, 18 iterations)",
+                          "gpu_s": tg, "cpu_s": tc, "cpu_cores": cores, "parity": {"pi_vector": rel(pi, g["pi_vector"])}}))
 
     if "c2" in want:
         from gaussian_process_b200 import CO2_example as C2
