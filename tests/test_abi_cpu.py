@@ -14,7 +14,8 @@ def test_header_parses_and_library_exports_every_symbol():
     assert len(protos) >= 35
     for must in ("gpx_create", "gpx_cov_build", "gpx_potrf", "gpx_trsv", "gpx_trsm", "gpx_trtri", "gpx_lauum", "gpx_gemm",
                  "gpx_lml", "gpx_lml_grad", "gpx_gp_fit", "gpx_gp_fit_grad", "gpx_host_lml", "gpx_logistic_terms",
-                 "gpx_build_B", "gpx_softmax_classes", "gpx_potrf_mg", "gpx_nccl_init"):
+                 "gpx_build_B", "gpx_softmax_classes", "gpx_potrf_mg", "gpx_nccl_init", "gpx_gp_small_posterior_host",
+                 "gpx_gp_small_fit_host", "gpx_gp_small_sample_host", "gpx_gp_small_lml_grad_host", "gpx_gp_small_ascent_host"):
         assert must in protos, must
     if not os.path.isfile(_lib.LIB_PATH):
         pytest.skip("libgpx.so not built (run __graft_entry__.build())")
@@ -29,6 +30,21 @@ def test_version_and_padding_without_gpu():
     lib = _lib.load()
     assert lib.gpx_version() == 100
     assert lib.gpx_padded_dim(1) == 128 and lib.gpx_padded_dim(128) == 128 and lib.gpx_padded_dim(129) == 256
+    assert lib.gpx_small_max() == 128
+
+
+def test_host_pointer_entry_points_reject_bad_arguments_without_gpu():
+    """Argument validation of the host-pointer calls happens before any CUDA work: NULL handle -> status -1."""
+    if not os.path.isfile(_lib.LIB_PATH):
+        pytest.skip("libgpx.so not built")
+    lib = _lib.load()
+    out = (ctypes.c_double * 8)()
+    x = (ctypes.c_double * 4)(0.0, 1.0, 2.0, 3.0)
+    th = (ctypes.c_double * 2)(1.0, 1.0)
+    assert lib.gpx_gp_small_lml_grad_host(None, 0, x, 4, 1, x, th, 2, 5e-4, out, None) == -1
+    assert lib.gpx_gp_small_ascent_host(None, x, 4, 1, x, 1.0, 1.0, 5e-4, 0.01, 1e-3, 10, out) == -1
+    assert lib.gpx_gp_small_sample_host(None, 4, 1, x, out) == -1
+    assert b"bad argument" in lib.gpx_last_error()
 
 
 def test_no_cpu_fallback():
