@@ -424,7 +424,10 @@ namespace {
 //                                   c. [after the bulk update j-1 finished] update block column j+2 with panel j
 //   bulk stream S                 : update block columns >= j+3 with panel j
 // so the latency-bound panel chain runs concurrently with (and up to two panels ahead of) the DMMA-bound bulk updates.
+int potrf_la_split(gpx_ctx* h, double* A, int64_t n, int64_t lda, double* dinv, int goff, int nb);
+int la_split();
 int potrf_la(gpx_ctx* h, double* A, int64_t n, int64_t lda, double* dinv, int goff, int nb) {
+    if (la_split() && h->aux2_stream) return potrf_la_split(h, A, n, lda, dinv, goff, nb);
     const int64_t nblk = n / nb;
     const int tpb = nb / LT;
     cudaStream_t S = h->stream, H = h->aux_stream;
@@ -495,6 +498,108 @@ int potrf_la(gpx_ctx* h, double* A, int64_t n, int64_t lda, double* dinv, int go
     }
     cudaEventDestroy(ev0);
     return rc;
+}
+
+// The same right-looking factorisation with the panel chain cut down to what the NEXT diagonal block really waits for.
+// With panel j final in its diagonal block (Linv_j known), only the first block row below it gates the next leaf:
+//   H  (chain, high priority): T_top(j): row block j+1 of column j  <- . Linv_j^T
+//                              U_diag(j->j+1): diagonal block j+1    -= L(j+1,j) L(j+1,j)^T
+//                              factor diagonal block j+1
+//   H2 (column work)         : T_rest(j): row blocks >= j+2 of column j;  U_rest(j->j+1): rows >= j+2 of column j+1;
+//                              U2(j->j+2): column j+2 (rows >= j+2)
+//   S  (bulk)                : columns >= j+3
+// so a chain step is {one-block TRSM, one-block SYRK, diagonal factorisation} instead of three column-high GEMMs plus the
+// factorisation.  Every block still receives its updates in panel order (S: panels <= c-3, H2: c-2, H2/H: c-1), hence the
+// result is bit-identical to potrf_la's.  Events: Leaf[j] (H), Top[j] (H), P[j] / U1[j] / U2[j] (H2), Sd[j] (S).
+int potrf_la_split(gpx_ctx* h, double* A, int64_t n, int64_t lda, double* dinv, int goff, int nb) {
+    const int64_t nblk = n / nb;
+    const int tpb = nb / LT;
+    cudaStream_t S = h->stream, H = h->aux_stream, H2 = h->aux2_stream;
+    enum { LEAF = 0, TOP, PAN, U1, U2, SD, NEV };
+    std::vector<cudaEvent_t> ev(NEV * nblk);
+    for (auto& e : ev) GPX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    auto E = [&](int kind, int64_t j) -> cudaEvent_t { return ev[kind * nblk + j]; };
+    int rc = 0;
+    auto rec = [&](int kind, int64_t j, cudaStream_t st) { if (rc == 0 && cudaEventRecord(E(kind, j), st) != cudaSuccess) rc = GPX_E_CUDA; };
+    auto wait = [&](cudaStream_t st, int kind, int64_t j) { if (rc == 0 && j >= 0 && cudaStreamWaitEvent(st, E(kind, j), 0) != cudaSuccess) rc = GPX_E_CUDA; };
+    auto on = [&](cudaStream_t st, auto&& fn) { if (rc != 0) return; h->stream = st; rc = fn(); h->stream = S; };
+    cudaEvent_t ev0;
+    GPX_CUDA(cudaEventCreateWithFlags(&ev0, cudaEventDisableTiming));
+    GPX_CUDA(cudaEventRecord(ev0, S));            // everything queued on S so far precedes the factorisation
+    GPX_CUDA(cudaStreamWaitEvent(H, ev0, 0));
+    GPX_CUDA(cudaStreamWaitEvent(H2, ev0, 0));
+    auto blk = [&](int64_t i, int64_t j) -> double* { return A + i * nb * lda + j * nb; };
+    auto dj = [&](int64_t j) -> double* { return dinv + j * tpb * LT * LT; };
+    // C(rows r0.., block column c) -= A(rows r0.., block column j) * A(block row c, block column j)^T
+    auto update = [&](int64_t j, int64_t r0, int64_t rows, int64_t c, int64_t ncols, int lower) -> int {
+        if (rows <= 0 || ncols <= 0) return 0;
+        GemmArgs a = base_args();
+        a.A = blk(r0, j); a.lda = lda; a.a_kmajor = 1;
+        a.B = blk(c, j); a.ldb = lda; a.b_kmajor = 1;
+        a.C = blk(r0, c); a.ldc = lda;
+        a.M = (int)(rows * nb); a.N = (int)(ncols * nb); a.K = nb;
+        a.alpha = -1.0; a.beta = 1.0;
+        a.lower_only = lower;
+        return gpx_gemm_launch(h, a);
+    };
+    on(H, [&]() { return potrf_rec(h, blk(0, 0), nb, lda, dj(0), goff); });
+    rec(LEAF, 0, H);
+    for (int64_t j = 0; j < nblk && rc == 0; ++j) {
+        const int64_t rest = nblk - (j + 2);       // block rows below block row j+1
+        // ---- H: the part of panel j the next diagonal block waits for
+        if (j + 1 < nblk) {
+            wait(H, U1, j - 1); wait(H, U2, j - 2); wait(H, SD, j - 3);          // block (j+1, j) has every earlier update
+            on(H, [&]() { return trsm_right_lt(h, blk(j + 1, j), nb, lda, blk(j, j), nb, lda, dj(j)); });
+            rec(TOP, j, H);
+            wait(H, U2, j - 1); wait(H, SD, j - 2);                              // block (j+1, j+1) likewise
+            on(H, [&]() {
+                GPX_TRY(update(j, j + 1, 1, j + 1, 1, 1));
+                return potrf_rec(h, blk(j + 1, j + 1), nb, lda, dj(j + 1), goff + (int)((j + 1) * nb));
+            });
+            rec(LEAF, j + 1, H);
+        }
+        // ---- H2: the rest of column j, then its updates of columns j+1 and j+2
+        if (rest > 0) {
+            wait(H2, LEAF, j); wait(H2, SD, j - 3);
+            on(H2, [&]() { return trsm_right_lt(h, blk(j + 2, j), rest * nb, lda, blk(j, j), nb, lda, dj(j)); });
+            rec(PAN, j, H2);
+            wait(H2, TOP, j); wait(H2, SD, j - 2);
+            on(H2, [&]() { return update(j, j + 2, rest, j + 1, 1, 0); });
+            rec(U1, j, H2);
+            wait(H2, SD, j - 1);
+            on(H2, [&]() { return update(j, j + 2, rest, j + 2, 1, 1); });
+            rec(U2, j, H2);
+        }
+        // ---- S: bulk update of the columns >= j+3
+        if (nblk - (j + 3) > 0) {
+            wait(S, PAN, j);
+            on(S, [&]() { return update(j, j + 3, nblk - (j + 3), j + 3, nblk - (j + 3), 1); });
+            rec(SD, j, S);
+        }
+    }
+    if (rc == 0) {   // join: S continues only after both chains have finished
+        cudaEventRecord(ev0, H);
+        cudaStreamWaitEvent(S, ev0, 0);
+        cudaEvent_t ev1;
+        if (cudaEventCreateWithFlags(&ev1, cudaEventDisableTiming) == cudaSuccess) {
+            cudaEventRecord(ev1, H2);
+            cudaStreamWaitEvent(S, ev1, 0);
+            cudaEventDestroy(ev1);
+        }
+    }
+    h->stream = S;
+    for (auto& e : ev) cudaEventDestroy(e);
+    cudaEventDestroy(ev0);
+    return rc;
+}
+
+int la_split() {   // 1: potrf_la_split (default), 0: potrf_la
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GPX_POTRF_LA_SPLIT");
+        v = e ? atoi(e) : 1;
+    }
+    return v;
 }
 
 int la_block(int64_t n) {   // panel width of the look-ahead algorithm
