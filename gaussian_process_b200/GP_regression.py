@@ -77,7 +77,11 @@ def f_prior(X_test, mu_prior, kernel_choice, kernel_parameter, num_fun):
     """Prior draws mu + chol(K + s I) z.  GP_regression.py:71-92."""
     eng = get_engine()
     kind, theta = _kind_theta(kernel_choice, kernel_parameter, 1.0)
-    Xd = eng.to_device(np.asarray(X_test, dtype=np.float64))
+    X_test = np.asarray(X_test, dtype=np.float64)
+    if FUSED_SMALL_PATH and num_fun >= 1 and X_test.shape[0] <= eng.small_max():
+        m = eng.small_prior_factor(kind, X_test, theta, NOISE_VARIANCE)      # one launch; raises like :90
+        return mu_prior + eng.small_sample(m, np.random.normal(size=(m, num_fun)))
+    Xd = eng.to_device(X_test)
     m = Xd.shape[0]
     B = eng.cov(kind, Xd, Xd, theta, diag_add=NOISE_VARIANCE, same_x=True)
     eng.potrf(B)

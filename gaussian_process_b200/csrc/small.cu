@@ -271,6 +271,36 @@ __global__ void __launch_bounds__(ST, 1) gp_small_kernel(const __grid_constant__
     if (tid == 0) { o_s[1] = 0.0; o_s[2] = 0.0; o_s[3] = 0.0; }
 }
 
+// Prior factor (GP_regression.py:71-92): chol(k(X*,X*) + s I) for n <= 128, left in `keep` as [L packed | 0] so that
+// gp_small_sample_kernel forms L z.  out[0] = 1-based index of a non-positive pivot or 0.
+template <int KIND>
+__global__ void __launch_bounds__(ST, 1) gp_small_prior_kernel(const __grid_constant__ CovParams p, int n, double s,
+                                                               const double* __restrict__ Xs, double* __restrict__ keep,
+                                                               double* __restrict__ out) {
+    extern __shared__ double sm[];
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const int D = p.D;
+    double* Lp = sm;
+    double* rdiag = Lp + n * (n + 1) / 2;
+    double* rinv = rdiag + n;
+    double* pinv = rinv + n;
+#pragma unroll 1
+    for (int ab = 0; ab < 16; ++ab) {
+        const int i = ty + 32 * (ab >> 2), j = tx + 32 * (ab & 3);
+        if (i < n && j <= i) {
+            double v = pair_value<KIND>(p, Xs + (size_t)i * D, Xs + (size_t)j * D, i == j);
+            if (i == j) v += s;
+            Lp[tri(i, j)] = v;
+        }
+    }
+    const int info = chol_packed(Lp, n, rdiag, rinv, pinv);
+    if (tid == 0) out[0] = info;
+    if (info) return;
+    const int np_ = n * (n + 1) / 2;
+    for (int t = tid; t < np_; t += ST) keep[t] = Lp[t];
+    for (int t = tid; t < n; t += ST) keep[np_ + t] = 0.0;
+}
+
 // f_post = mu + L_ Z from the factor kept by a mode-2 launch (GP_regression.py:155).
 __global__ void __launch_bounds__(ST) gp_small_sample_kernel(int n, int nf, const double* __restrict__ keep,
                                                              const double* __restrict__ Z, double* __restrict__ fpost) {
@@ -626,5 +656,61 @@ extern "C" int gpx_gp_small_ascent_host(gpx_handle h, const double* X, int64_t N
     out6[3] = out[0];   // LML of the last iteration
     out6[4] = out[5];   // |LML - LML_old| of the last iteration
     out6[5] = out[6];   // 1 when the tolerance was met
+    return 0;
+}
+
+namespace {
+template <int KIND>
+int launch_small_prior(gpx_ctx* h, const CovParams& p, int n, double s, const double* Xs, double* keep, double* out, size_t smem) {
+    static bool configured = false;
+    if (!configured) {
+        GPX_CUDA(cudaFuncSetAttribute(gp_small_prior_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    gp_small_prior_kernel<KIND><<<1, ST, smem, h->stream>>>(p, n, s, Xs, keep, out);
+    GPX_CHECK_LAUNCH(h);
+    return 0;
+}
+}  // namespace
+
+extern "C" int gpx_gp_small_prior_factor_host(gpx_handle h, int kind, const double* Xs, int64_t n, int D, const double* theta,
+                                              int ntheta, double s) {
+    GPX_REQUIRE(h != nullptr, 1);
+    GPX_REQUIRE(kind >= 0 && kind <= 3, 2);
+    GPX_REQUIRE(Xs != nullptr && theta != nullptr, 3);
+    GPX_REQUIRE(n >= 1 && n <= SMAX, 4);
+    GPX_REQUIRE(D >= 1, 5);
+    CovParams p;
+    {
+        static const int expect[4] = {2, 1, 2, 11};
+        GPX_REQUIRE(expect[kind] == ntheta, 7);
+        p.kind = kind;
+        p.ntheta = ntheta;
+        p.D = D;
+        for (int i = 0; i < 11; ++i) p.th[i] = i < ntheta ? theta[i] : 0.0;
+    }
+    const size_t nXs = (size_t)n * D;
+    const size_t smem = ((size_t)n * (n + 1) / 2 + 3 * (size_t)n) * sizeof(double);
+    GPX_TRY(ensure_pinned(h, (nXs + 1) * sizeof(double)));
+    void* dev = nullptr;
+    GPX_TRY(gpx_scratch(h, (nXs + 1) * sizeof(double), &dev));
+    if (!h->d_small) GPX_CUDA(cudaMalloc(&h->d_small, ((size_t)SMAX * (SMAX + 1) / 2 + SMAX) * sizeof(double)));
+    h->small_n = 0;
+    double* hin = (double*)h->pinned;
+    double* din = (double*)dev;
+    memcpy(hin, Xs, nXs * sizeof(double));
+    GPX_CUDA(cudaMemcpyAsync(din, hin, nXs * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    int r;
+    switch (kind) {
+        case GPX_COV_SE: r = launch_small_prior<GPX_COV_SE>(h, p, (int)n, s, din, h->d_small, din + nXs, smem); break;
+        case GPX_COV_LIN: r = launch_small_prior<GPX_COV_LIN>(h, p, (int)n, s, din, h->d_small, din + nXs, smem); break;
+        case GPX_COV_PER: r = launch_small_prior<GPX_COV_PER>(h, p, (int)n, s, din, h->d_small, din + nXs, smem); break;
+        default: r = launch_small_prior<GPX_COV_CO2>(h, p, (int)n, s, din, h->d_small, din + nXs, smem); break;
+    }
+    if (r != 0) return r;
+    GPX_CUDA(cudaMemcpyAsync(hin + nXs, din + nXs, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    GPX_CUDA(cudaStreamSynchronize(h->stream));
+    if (hin[nXs] != 0.0) return (int)hin[nXs];      // K + s I not positive definite (GP_regression.py:90)
+    h->small_n = (int)n;
     return 0;
 }

@@ -353,6 +353,15 @@ class Engine:
         check(st, "gpx_gp_small_fit_host")
         return mu, var, float(lml.value)
 
+    def small_prior_factor(self, kind: int, Xs, theta, s: float) -> int:
+        """chol(k(Xs,Xs) + s I) in one launch, kept on the device for small_sample (GP_regression.py:71-92)."""
+        self._sync_stream()
+        Xs = np.ascontiguousarray(Xs, dtype=np.float64)
+        th, thp = _theta_array(theta)
+        check(self.lib.gpx_gp_small_prior_factor_host(self.h, kind, ctypes.c_void_p(Xs.ctypes.data), Xs.shape[0], Xs.shape[1],
+                                                      thp, len(th), float(s)), "gpx_gp_small_prior_factor_host")
+        return Xs.shape[0]
+
     def small_sample(self, n: int, Z) -> np.ndarray:
         """Second half: mu + L_ Z for the factor kept by the last small_fit (Z: (n, num_fun) standard normals)."""
         Z = np.ascontiguousarray(Z, dtype=np.float64)

@@ -238,6 +238,11 @@ int gpx_gp_small_fit_host(gpx_handle h, int kind, const double* X, int64_t N, in
                           int64_t n, const double* theta, int ntheta, double s, double jitter, double* mu, double* var,
                           double* lml);
 int gpx_gp_small_sample_host(gpx_handle h, int64_t n, int nf, const double* Z, double* fpost);
+/* Prior draws (GP_regression.py:71-92) for n <= gpx_small_max(): factor k(Xs,Xs) + s I in one launch and keep it on the
+ * device; gpx_gp_small_sample_host(h, n, nf, Z, out) then returns L Z (the caller adds its prior mean).  Returns > 0
+ * when the matrix is not positive definite (:90). */
+int gpx_gp_small_prior_factor_host(gpx_handle h, int kind, const double* Xs, int64_t n, int D, const double* theta,
+                                   int ntheta, double s);
 /* LML (tune...:292-313, CO2...:131-149) and, when grad != NULL, dLML/dtheta for every hyper-parameter
  * (tune...:31-64,144 generalised per SURVEY Appendix C) for N <= gpx_small_max() in one kernel launch. */
 int gpx_gp_small_lml_grad_host(gpx_handle h, int kind, const double* X, int64_t N, int D, const double* y,

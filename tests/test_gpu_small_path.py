@@ -237,3 +237,31 @@ def test_small_lml_not_positive_definite_raises():
     X, y, _ = O.synth_c1(10, 5)
     with pytest.raises(np.linalg.LinAlgError):
         get_engine().small_lml_grad(COV_SE, X, y, [1.0, 1.0], -3.0)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_prior_draws_both_paths(G, golden, fused):
+    """GP_regression.f_prior (:71-92): golden draws of the unmodified reference; the fused path factors
+    k(X*,X*) + s I in one launch and forms L z in a second."""
+    from gaussian_process_b200 import get_engine
+    G.FUSED_SMALL_PATH = fused
+    g = golden("ka1_regression.npz")
+    Xs = g["n5_Xs"]
+    np.random.seed(11)
+    before = get_engine().launches()
+    fp = G.f_prior(Xs, np.zeros((100, 1)), "rbf", 1, 3)
+    if fused:
+        assert get_engine().launches() - before == 2
+    assert fp.shape == (100, 3) and rel(fp, g["n5_fprior"]) < 1e-8
+    np.random.seed(4)
+    per = G.f_prior(Xs, np.ones((100, 1)), "per", [2.0, 1.5], 2)
+    np.random.seed(4)
+    assert rel(per, O.f_prior(Xs, np.ones((100, 1)), "per", [2.0, 1.5], 2)) < 1e-7
+    # a negative "noise" makes K + s I indefinite: LinAlgError, as np.linalg.cholesky at :90
+    old = G.NOISE_VARIANCE
+    try:
+        G.NOISE_VARIANCE = -2.0
+        with pytest.raises(np.linalg.LinAlgError):
+            G.f_prior(Xs, np.zeros((100, 1)), "rbf", 1, 1)
+    finally:
+        G.NOISE_VARIANCE = old
