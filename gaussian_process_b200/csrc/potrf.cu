@@ -418,6 +418,24 @@ __global__ void copy_tiles_kernel(double* __restrict__ dst, int64_t ldd, int64_t
 
 
 namespace {
+// Events of one factorisation; destroyed on every exit path (destroying a pending event only defers its release).
+struct EventSet {
+    std::vector<cudaEvent_t> ev;
+    int create(size_t count) {
+        ev.assign(count, nullptr);
+        for (auto& e : ev)
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+                gpx_set_error("potrf: cudaEventCreate failed");
+                return GPX_E_CUDA;
+            }
+        return 0;
+    }
+    ~EventSet() {
+        for (auto e : ev)
+            if (e) cudaEventDestroy(e);
+    }
+};
+
 // Right-looking blocked Cholesky with LOOK-AHEAD on two streams (used below a size threshold where the serial chain of
 // small kernels, not the DMMA pipe, bounds the recursive formulation).  Panel width nb; after panel j is final:
 //   chain stream H (high priority): a. update block column j+1 with panel j   b. factor panel j+1 (diag potrf + TRSM)
@@ -431,13 +449,11 @@ int potrf_la(gpx_ctx* h, double* A, int64_t n, int64_t lda, double* dinv, int go
     const int64_t nblk = n / nb;
     const int tpb = nb / LT;
     cudaStream_t S = h->stream, H = h->aux_stream;
-    std::vector<cudaEvent_t> evP(nblk), evS(nblk);
-    for (int64_t j = 0; j < nblk; ++j) {
-        GPX_CUDA(cudaEventCreateWithFlags(&evP[j], cudaEventDisableTiming));
-        GPX_CUDA(cudaEventCreateWithFlags(&evS[j], cudaEventDisableTiming));
-    }
-    cudaEvent_t ev0;
-    GPX_CUDA(cudaEventCreateWithFlags(&ev0, cudaEventDisableTiming));
+    EventSet es;
+    GPX_TRY(es.create(2 * nblk + 1));
+    cudaEvent_t* evP = es.ev.data();
+    cudaEvent_t* evS = evP + nblk;
+    cudaEvent_t ev0 = es.ev[2 * nblk];
     GPX_CUDA(cudaEventRecord(ev0, S));            // everything queued on S so far (covariance build ...) precedes the chain
     GPX_CUDA(cudaStreamWaitEvent(H, ev0, 0));
     auto on_H = [&](auto&& fn) -> int { h->stream = H; int r = fn(); h->stream = S; return r; };
@@ -491,13 +507,7 @@ int potrf_la(gpx_ctx* h, double* A, int64_t n, int64_t lda, double* dinv, int go
         cudaStreamWaitEvent(S, ev0, 0);
     }
     h->stream = S;
-    // no host synchronisation: destroying an event that is still pending only defers the release of its resources
-    for (int64_t j = 0; j < nblk; ++j) {
-        cudaEventDestroy(evP[j]);
-        cudaEventDestroy(evS[j]);
-    }
-    cudaEventDestroy(ev0);
-    return rc;
+    return rc;   // no host synchronisation; EventSet releases the events
 }
 
 // The same right-looking factorisation with the panel chain cut down to what the NEXT diagonal block really waits for.
@@ -516,15 +526,14 @@ int potrf_la_split(gpx_ctx* h, double* A, int64_t n, int64_t lda, double* dinv, 
     const int tpb = nb / LT;
     cudaStream_t S = h->stream, H = h->aux_stream, H2 = h->aux2_stream;
     enum { LEAF = 0, TOP, PAN, U1, U2, SD, NEV };
-    std::vector<cudaEvent_t> ev(NEV * nblk);
-    for (auto& e : ev) GPX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    auto E = [&](int kind, int64_t j) -> cudaEvent_t { return ev[kind * nblk + j]; };
+    EventSet es;
+    GPX_TRY(es.create(NEV * nblk + 2));
+    auto E = [&](int kind, int64_t j) -> cudaEvent_t { return es.ev[kind * nblk + j]; };
     int rc = 0;
     auto rec = [&](int kind, int64_t j, cudaStream_t st) { if (rc == 0 && cudaEventRecord(E(kind, j), st) != cudaSuccess) rc = GPX_E_CUDA; };
     auto wait = [&](cudaStream_t st, int kind, int64_t j) { if (rc == 0 && j >= 0 && cudaStreamWaitEvent(st, E(kind, j), 0) != cudaSuccess) rc = GPX_E_CUDA; };
     auto on = [&](cudaStream_t st, auto&& fn) { if (rc != 0) return; h->stream = st; rc = fn(); h->stream = S; };
-    cudaEvent_t ev0;
-    GPX_CUDA(cudaEventCreateWithFlags(&ev0, cudaEventDisableTiming));
+    cudaEvent_t ev0 = es.ev[NEV * nblk], ev1 = es.ev[NEV * nblk + 1];
     GPX_CUDA(cudaEventRecord(ev0, S));            // everything queued on S so far precedes the factorisation
     GPX_CUDA(cudaStreamWaitEvent(H, ev0, 0));
     GPX_CUDA(cudaStreamWaitEvent(H2, ev0, 0));
@@ -580,17 +589,11 @@ int potrf_la_split(gpx_ctx* h, double* A, int64_t n, int64_t lda, double* dinv, 
     if (rc == 0) {   // join: S continues only after both chains have finished
         cudaEventRecord(ev0, H);
         cudaStreamWaitEvent(S, ev0, 0);
-        cudaEvent_t ev1;
-        if (cudaEventCreateWithFlags(&ev1, cudaEventDisableTiming) == cudaSuccess) {
-            cudaEventRecord(ev1, H2);
-            cudaStreamWaitEvent(S, ev1, 0);
-            cudaEventDestroy(ev1);
-        }
+        cudaEventRecord(ev1, H2);
+        cudaStreamWaitEvent(S, ev1, 0);
     }
     h->stream = S;
-    for (auto& e : ev) cudaEventDestroy(e);
-    cudaEventDestroy(ev0);
-    return rc;
+    return rc;   // no host synchronisation; EventSet releases the events
 }
 
 int la_split() {   // 1: potrf_la_split (default), 0: potrf_la
