@@ -497,9 +497,3 @@ extern "C" int gpx_mg_emulate_fit_grad(gpx_handle h, int P, int kind, const doub
     }
     return 0;
 }
-
-extern "C" int gpx_potrf_mg(gpx_handle h, double* Aloc, int64_t n, int64_t ldl, int64_t nb, double* panel, double* dinv) {
-    (void)h; (void)Aloc; (void)n; (void)ldl; (void)nb; (void)panel; (void)dinv;
-    gpx_set_error("gpx_potrf_mg: superseded by gpx_mg_fit_grad (block-cyclic Cholesky is driven from there)");
-    return GPX_E_ARG;
-}

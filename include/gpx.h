@@ -212,8 +212,8 @@ int gpx_mg_fit_grad(gpx_handle h, int kind, const double* X, int64_t n, int D, c
 int gpx_mg_emulate_fit_grad(gpx_handle h, int P, int kind, const double* X, int64_t n, int D, const double* theta_host,
                             int ntheta, double s, const double* y, int nb, double* ws_all, double* alpha, double* out3,
                             double* grad);
-/* legacy name kept for ABI stability: returns GPX_E_ARG (use gpx_mg_fit_grad) */
-int gpx_potrf_mg(gpx_handle h, double* Aloc, int64_t n, int64_t ldl, int64_t nb, double* panel, double* dinv);
+/* The distributed (block-cyclic) Cholesky of SURVEY 8e is the factorisation phase of gpx_mg_fit_grad: with_grad = 0 stops
+ * after factor + alpha + LML, so there is no separate gpx_potrf_mg entry point. */
 
 /* ---- host-buffer drop-in calls (HOST pointers; copies inside; synchronous) ------------------*/
 /* LML (+ optional gradient wrt all theta when grad_host != NULL) of y ~ GP(0, cov + s I). */

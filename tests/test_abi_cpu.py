@@ -14,7 +14,7 @@ def test_header_parses_and_library_exports_every_symbol():
     assert len(protos) >= 35
     for must in ("gpx_create", "gpx_cov_build", "gpx_potrf", "gpx_trsv", "gpx_trsm", "gpx_trtri", "gpx_lauum", "gpx_gemm",
                  "gpx_lml", "gpx_lml_grad", "gpx_gp_fit", "gpx_gp_fit_grad", "gpx_host_lml", "gpx_logistic_terms",
-                 "gpx_build_B", "gpx_softmax_classes", "gpx_potrf_mg", "gpx_nccl_init", "gpx_gp_small_posterior_host",
+                 "gpx_build_B", "gpx_softmax_classes", "gpx_mg_fit_grad", "gpx_nccl_init", "gpx_gp_small_posterior_host",
                  "gpx_gp_small_fit_host", "gpx_gp_small_sample_host", "gpx_gp_small_lml_grad_host", "gpx_gp_small_ascent_host", "gpx_gp_small_prior_factor_host"):
         assert must in protos, must
     if not os.path.isfile(_lib.LIB_PATH):
