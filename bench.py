@@ -311,7 +311,7 @@ def run_gpx(args):
     if rank != 0:
         return
     cpu = cpu_best = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # the CPU legs are timed on rank 0 at N=1 only
         t, scaled, lml_c, grad_c = cpu_reference_sample(args.cpu_sample_n, D, n)
         cpu = {"value": scaled, "unit": "s", "cores": host_threads(), "kind": "port",
                "sample": "oracle port (NumPy/OpenBLAS) one LML+grad iteration at N=%d D=%d took %.2f s; scaled by (%d/%d)^3"
