@@ -8,10 +8,10 @@ package (``gaussian_process_b200``) never imports anything from ``oracle/`` and 
 its CUDA library is missing.
 
 Pinning: the reference ships no tests or golden vectors.  This restatement is pinned by
-(i) ``tests/test_oracle_vs_reference.py`` which runs the *unmodified* reference functions
-(through ``oracle/ref_loader.py``) against every function here on seeded inputs (build container
-only) and (ii) ``tests/golden/*.npz`` generated from the reference by ``oracle/gen_golden.py``
-(committed; checked everywhere).
+(i) ``tests/test_oracle.py::test_oracle_matches_live_reference_*`` which run the *unmodified*
+reference functions (through ``oracle/ref_loader.py``) against the functions here on seeded inputs
+(build container only: /root/reference does not exist on the GPU box) and (ii) ``tests/golden/*.npz``
+generated from the reference by ``oracle/gen_golden.py`` (committed; checked everywhere).
 
 Every function cites the reference file:line it follows.  Linear algebra deliberately uses the same
 NumPy entry points as the reference (``np.linalg.cholesky / solve / inv``, ``np.dot``) so that the
