@@ -222,3 +222,54 @@ def test_oracle_matches_live_reference_classifiers():
     pv, pm = M.compute_pi(f, 3, 60)
     pv2, pm2 = O.compute_pi(f, 3, 60)
     assert rel(pv2, pv) < 1e-15 and rel(pm2, pm) < 1e-15
+
+
+@needs_ref
+def test_oracle_matches_live_reference_on_random_shapes():
+    """Property-style pinning: 20 seeded random sizes / dimensions / hyper-parameters, every regression-path function
+    of the oracle against the unmodified reference (prediction, lin / per kernels, CO2 LML and prediction, SE LML)."""
+    R = load_reference()
+    G, T, C2 = R["GP_regression"], R["tune_hyperparms_regression"], R["CO2_example"]
+    cfg = np.random.RandomState(2024)
+    for case in range(20):
+        N, n, D = int(cfg.randint(2, 41)), int(cfg.randint(1, 31)), int(cfg.randint(1, 6))
+        l, nf, seed = float(cfg.uniform(0.4, 3.0)), int(cfg.randint(1, 5)), int(cfg.randint(0, 10 ** 6))
+        rs = np.random.RandomState(seed)
+        X, Xs = rs.uniform(-3, 3, (N, D)), rs.uniform(-3, 3, (n, D))
+        y = np.sin(X.sum(1)) + 0.05 * rs.randn(N)
+        np.random.seed(seed)
+        mu, sd, fp = O.regression_prediction(X, Xs, y, 'rbf', l, nf)
+        np.random.seed(seed)
+        mu_r, sd_r, fp_r = G.prediction(X, Xs, y, 'rbf', l, nf)
+        assert rel(mu, mu_r) < 1e-12 and rel(fp, fp_r) < 1e-9, case
+        assert np.allclose(sd ** 2, sd_r ** 2, rtol=0, atol=1e-12, equal_nan=True), case
+        assert rel(O.lin_kernel(X, Xs, l), G.lin_kernel(X, Xs, l)) < 1e-14, case
+        x1, xs1 = X[:, :1], Xs[:, :1]
+        assert rel(O.per_kernel(x1, xs1, [2.0, l]), G.per_kernel(x1, xs1, [2.0, l])) < 1e-14, case
+        # CO2 composite on time-like 1-D inputs (its real use).  With theta_1 = 66 some draws are numerically
+        # indefinite: then BOTH sides raise LinAlgError (CO2_example.py:143 / :212); otherwise the numbers agree.
+        t = 1958 + np.sort(rs.uniform(0, 40, N))[:, None]
+        ts = 1998 + np.sort(rs.uniform(0, 5, n))[:, None]
+        yt = 3 * np.sin(2 * np.pi * t.ravel()) + 0.1 * (t.ravel() - 1958) ** 2 + 0.3 * rs.randn(N)
+        yt -= yt.mean()
+        th = O.CO2_THETA_BOOK * (0.7 + 0.6 * rs.rand(11))
+
+        def both(fo, fr, *a):
+            outs = []
+            for fn in (fo, fr):
+                np.random.seed(seed)
+                try:
+                    with np.errstate(invalid="ignore"):
+                        outs.append(fn(*a))
+                except np.linalg.LinAlgError:
+                    outs.append(None)
+            assert (outs[0] is None) == (outs[1] is None), case
+            return outs
+
+        lo, lr = both(O.co2_lml, C2.compute_mar_likelihood, t, yt, th)
+        if lo is not None:
+            assert rel(lo, lr) < 1e-10, case
+        po, pr = both(O.co2_make_prediction, C2.make_prediction, t, ts, yt, th)
+        if po is not None:
+            assert rel(po[0], pr[0]) < 1e-9 and np.allclose(po[1] ** 2, pr[1] ** 2, rtol=1e-8, atol=1e-8, equal_nan=True), case
+        assert rel(O.rbf_lml(X, y, 1.0, l), T.compute_mar_likelihood(X, None, y, 1.0, l)) < 1e-12, case
