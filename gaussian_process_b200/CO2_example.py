@@ -30,6 +30,42 @@ def _theta(hyperparms):
     return t
 
 
+def _co2_term(term, sqdist, l2_norm, t0, t1, t2):
+    import ctypes
+    eng = get_engine()
+    d2 = np.ascontiguousarray(sqdist, dtype=np.float64)
+    if d2.ndim != 2:
+        raise ValueError("sqdist must be a matrix")
+    D2 = eng.to_device(d2)
+    R = eng.to_device(np.ascontiguousarray(l2_norm, dtype=np.float64)) if l2_norm is not None else None
+    out = eng.empty(*d2.shape)
+    eng._sync_stream()
+    from ._lib import check
+    check(eng.lib.gpx_co2_term(eng.h, term, d2.shape[0], d2.shape[1], eng._p(D2), d2.shape[1], eng._p(R), d2.shape[1],
+                               float(t0), float(t1), float(t2), eng._p(out), d2.shape[1]), "gpx_co2_term")
+    return eng.to_host(out)
+
+
+def kernel_1(sqdist, theta_1, theta_2):
+    """theta_1^2 exp(-.5 sqdist / theta_2^2)  (CO2...:9-17) as an element-wise device map."""
+    return _co2_term(1, sqdist, None, theta_1, theta_2, 0.0)
+
+
+def kernel_2(l2_norm, sqdist, theta_3, theta_4, theta_5):
+    """theta_3^2 exp(-.5 sqdist/theta_4^2 - 2 (sin(pi l2_norm)/theta_5)^2)  (CO2...:20-32)."""
+    return _co2_term(2, sqdist, l2_norm, theta_3, theta_4, theta_5)
+
+
+def kernel_3(sqdist, theta_6, theta_7, theta_8):
+    """theta_6^2 (1 + .5 sqdist/(theta_8 theta_7^2))^-theta_8  (CO2...:35-46)."""
+    return _co2_term(3, sqdist, None, theta_6, theta_7, theta_8)
+
+
+def kernel_4(sqdist, theta_9, theta_10, theta_11):
+    """theta_9^2 exp(-.5 sqdist/theta_10^2) + theta_11^2 I for a square block  (CO2...:49-66)."""
+    return _co2_term(4, sqdist, None, theta_9, theta_10, theta_11)
+
+
 def covariance_function(a, b, hyperparms):
     """K = k1 + k2 + k3 + k4 for inputs of any dimension (CO2...:69-94); the theta_11^2 delta term is
     added iff the block is square (:60-63), exactly as in the reference."""

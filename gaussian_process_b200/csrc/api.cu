@@ -52,6 +52,13 @@ extern "C" int gpx_create(int device, gpx_handle* out) {
     return 0;
 }
 
+int gpx_enter(gpx_ctx* h) {
+    int cur = -1;
+    GPX_CUDA(cudaGetDevice(&cur));
+    if (cur != h->device) GPX_CUDA(cudaSetDevice(h->device));
+    return 0;
+}
+
 extern "C" int gpx_destroy(gpx_handle h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
@@ -73,13 +80,13 @@ extern "C" int gpx_destroy(gpx_handle h) {
 }
 
 extern "C" int gpx_set_stream(gpx_handle h, void* s) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     h->stream = (cudaStream_t)s;
     return 0;
 }
 
 extern "C" int gpx_synchronize(gpx_handle h) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     GPX_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -136,7 +143,7 @@ int gpx_read_info(gpx_ctx* h, int* info_host) {
 extern "C" int gpx_gp_fit(gpx_handle h, int kind, const double* X, int64_t n, int D, const double* theta_host, int ntheta,
                           double s, const double* y, double* A, int64_t np_, int64_t lda, double* dinv, double* alpha,
                           double* out3) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     GPX_REQUIRE(np_ == gpx_padded_dim(n), 11);
     // K + s I, lower tiles only, identity padding            (tune...:306-307, CO2...:142-143)
     gpx_phase_mark(h, GPX_PH_COV);
@@ -188,7 +195,7 @@ extern "C" int gpx_gp_fit_grad(gpx_handle h, int kind, const double* X, int64_t 
 
 extern "C" int gpx_host_lml(gpx_handle h, int kind, const double* X, int64_t n, int D, const double* theta, int ntheta,
                             double s, const double* y, double* lml_out, double* grad_host) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     GPX_REQUIRE(n > 0, 4);
     const int64_t np_ = gpx_padded_dim(n);
     const int64_t nt = np_ / GPX_T;
@@ -294,7 +301,7 @@ __global__ void __launch_bounds__(1024, 1) mixed_peak_kernel(int iters, double* 
 }  // namespace
 
 extern "C" int gpx_bench_fp64_peak(gpx_handle h, int use_dmma, int iters, double* tflops_out, double* ms_out) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     cudaEvent_t e0, e1;
     GPX_CUDA(cudaEventCreate(&e0));
     GPX_CUDA(cudaEventCreate(&e1));

@@ -67,6 +67,17 @@ void gpx_set_error(const char* fmt, ...);
         }                                                                                    \
     } while (0)
 
+// every extern "C" entry point: validate the handle and make its device current (a process may hold handles on
+// several GPUs; kernel attributes, streams and allocations are per device)
+#define GPX_MAX_DEVICES 64
+int gpx_enter(gpx_ctx* h);
+#define GPX_ENTER(h)                                                                         \
+    do {                                                                                     \
+        GPX_REQUIRE((h) != nullptr, 1);                                                      \
+        int e__ = gpx_enter(h);                                                              \
+        if (e__ != 0) return e__;                                                            \
+    } while (0)
+
 #define GPX_TRY(call)                                                                        \
     do {                                                                                     \
         int r__ = (call);                                                                    \

@@ -244,10 +244,50 @@ int launch_build(gpx_ctx* h, const CovParams& p, const double* X1, int64_t n1, c
 
 }  // namespace
 
+namespace {
+// The four additive terms of the CO2 composite as element-wise maps of a precomputed squared-distance matrix
+// (CO2_example.py:9-66: kernel_1 .. kernel_4 take `sqdist` / `l2_norm`, not the inputs).  Same operation order as cov_eval.
+__global__ void __launch_bounds__(256) co2_term_kernel(int term, int64_t rows, int64_t cols, const double* __restrict__ D2,
+                                                      int64_t ldd, const double* __restrict__ R, int64_t ldr, double t0, double t1,
+                                                      double t2, int delta, double* __restrict__ out, int64_t ldo) {
+    const int64_t r = blockIdx.x;
+    for (int64_t c = (int64_t)blockIdx.y * 256 + threadIdx.x; c < cols; c += (int64_t)gridDim.y * 256) {
+        const double d = D2[r * ldd + c];
+        double v;
+        if (term == 1) {
+            v = (t0 * t0) * exp(-.5 * d / (t1 * t1));                                   // :17
+        } else if (term == 2) {
+            const double rr = R ? R[r * ldr + c] : sqrt(d);
+            const double q = sin(gpx_cov::PI_D * rr) / t2;
+            v = (t0 * t0) * exp(-.5 * d / (t1 * t1) + -2.0 * (q * q));                  // :30-32
+        } else if (term == 3) {
+            const double u = 1.0 + .5 * d / (t2 * (t1 * t1));                           // :44
+            v = (t0 * t0) * (1.0 / pow(u, t2));                                         // :45-46
+        } else {
+            v = (t0 * t0) * exp(-.5 * d / (t1 * t1));                                   // :65
+            if (delta && r == c) v += t2 * t2;                                          // :60-66 (delta iff square)
+        }
+        out[r * ldo + c] = v;
+    }
+}
+}  // namespace
+
+extern "C" int gpx_co2_term(gpx_handle h, int term, int64_t rows, int64_t cols, const double* sqdist, int64_t ldd,
+                            const double* l2_norm, int64_t ldr, double t0, double t1, double t2, double* out, int64_t ldo) {
+    GPX_ENTER(h);
+    GPX_REQUIRE(term >= 1 && term <= 4, 2);
+    GPX_REQUIRE(rows > 0 && cols > 0, 3);
+    GPX_REQUIRE(sqdist != nullptr && out != nullptr, 5);
+    dim3 grid((unsigned)rows, (unsigned)((cols + 255) / 256 > 64 ? 64 : (cols + 255) / 256));
+    co2_term_kernel<<<grid, 256, 0, h->stream>>>(term, rows, cols, sqdist, ldd, l2_norm, ldr, t0, t1, t2, rows == cols ? 1 : 0, out, ldo);
+    GPX_CHECK_LAUNCH(h);
+    return 0;
+}
+
 extern "C" int gpx_cov_build(gpx_handle h, int kind, const double* X1, int64_t n1, const double* X2, int64_t n2, int D,
                              const double* theta_host, int ntheta, double diag_add, int flags, double* K, int64_t n1p,
                              int64_t n2p, int64_t ldk, double* dK, int64_t dk_stride) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     GPX_REQUIRE(kind >= 0 && kind <= 3, 2);
     GPX_REQUIRE(n1 > 0 && n2 > 0, 4);
     GPX_REQUIRE(n1p >= n1 && n1p % TM == 0 && n2p >= n2 && n2p % TN == 0, 13);
@@ -302,7 +342,7 @@ int gpx_cov_build_block(gpx_ctx* h, int kind, const double* X, int64_t n, int D,
 
 extern "C" int gpx_lml_grad(gpx_handle h, int kind, const double* X, int64_t n, int D, const double* theta_host, int ntheta,
                             const double* Kinv, int64_t ldk, const double* alpha, double* grad) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     const int64_t np_ = ((n + TM - 1) / TM) * TM;
     return gpx_lml_grad_block(h, kind, X, n, D, theta_host, ntheta, Kinv, ldk, alpha, grad, np_, np_, 0, 0);
 }

@@ -206,7 +206,8 @@ double exec_flops(const GemmArgs& a, int TN) {
 template <bool A_KM, bool B_KM, int TN>
 int launch_t(gpx_ctx* h, const GemmArgs& a) {
     using C_ = Cfg<TN>;
-    static bool configured = false;
+    static bool configured_dev[GPX_MAX_DEVICES] = {};
+    bool& configured = configured_dev[h->device % GPX_MAX_DEVICES];   // cudaFuncSetAttribute is per device
     if (!configured) {
         GPX_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<A_KM, B_KM, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM));
         GPX_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<A_KM, B_KM, TN>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -256,7 +257,7 @@ int gpx_gemm_launch(gpx_ctx* h, const GemmArgs& a) {
 
 extern "C" int gpx_gemm(gpx_handle h, int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K, double alpha,
                         const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     GemmArgs a{};
     a.A = A; a.B = B; a.C = C;
     a.M = (int)M; a.N = (int)N; a.K = (int)K;

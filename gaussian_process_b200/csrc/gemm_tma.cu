@@ -217,9 +217,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
-int g_tma_state = 0;   // 0 unknown, 1 usable, -1 unavailable / disabled
+int g_tma_state_dev[GPX_MAX_DEVICES] = {};   // per device: 0 unknown, 1 usable, -1 unavailable / disabled
 
-int tma_init() {
+int tma_init(int device) {
+    int& g_tma_state = g_tma_state_dev[device % GPX_MAX_DEVICES];
     if (g_tma_state != 0) return g_tma_state;
     const char* e = getenv("GPX_GEMM_TMA");
     if (e && atoi(e) == 0) return g_tma_state = -1;
@@ -272,7 +273,7 @@ int make_map(CUtensorMap* m, const double* ptr, int64_t rows, int64_t K, int64_t
 int gpx_gemm_tma_try_launch(gpx_ctx* h, const GemmArgs& a, double flops_exec) {
     if (a.batch > 1 || a.batch2 > 1 || a.C == a.A || a.C == a.B) return 0;
     if ((a.lda % 2) || (a.ldb % 2)) return 0;
-    if (tma_init() != 1) return 0;
+    if (tma_init(h->device) != 1) return 0;
     constexpr int TN = 64;
     alignas(64) CUtensorMap mapA, mapB;
     const int64_t rowsB = a.cyc_P > 0 && a.cyc_b_rows ? a.M : a.N;

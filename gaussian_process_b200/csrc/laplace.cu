@@ -31,24 +31,30 @@ __global__ void logistic_terms_kernel(int mode, int64_t n, const double* __restr
 // B = I + diag(sw) K diag(sw) on the true n x n block; identity on the padding.
 __global__ void __launch_bounds__(256) build_B_kernel(const double* __restrict__ K, const double* __restrict__ sw, int64_t n,
                                                      int64_t np_, int64_t ld, double* __restrict__ B) {
-    const int64_t r = blockIdx.y;
+    const int64_t r = blockIdx.x;   // rows on grid.x (grid.y is limited to 65535, and N = 65536 is a headline size)
     const double sr = r < n ? sw[r] : 0.0;
-    for (int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x; c < np_; c += (int64_t)gridDim.x * 256) {
+    for (int64_t c = (int64_t)blockIdx.y * 256 + threadIdx.x; c < np_; c += (int64_t)gridDim.y * 256) {
         double v = (r == c) ? 1.0 : 0.0;
         if (r < n && c < n) v += sr * K[r * ld + c] * sw[c];
         B[r * ld + c] = v;
     }
 }
 
-// softmax over classes for every point (GP_multi_classification.py:26-33 applied per point :51-58)
+// softmax over classes for every point (GP_multi_classification.py:26-33 applied per point :51-58).  One thread per
+// OUTPUT index k = c*stride + i.  With stride < n (the reference's literal 60 when n > 60) several (c, i) pairs map to
+// the same k; the reference's sequential loop (i outer, c inner) leaves the value of the pair with the largest i, i.e.
+// the smallest c -- reproduced here deterministically instead of racing.
 __global__ void softmax_classes_kernel(int C, int64_t n, int64_t stride, const double* __restrict__ f, double* __restrict__ pi) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= (int64_t)(C - 1) * stride + n) return;
+    int64_t cw = k - (n - 1) > 0 ? (k - (n - 1) + stride - 1) / stride : 0;   // smallest class whose point index is < n
+    const int64_t i = k - cw * stride;
+    if (i < 0 || cw >= C) return;                                            // gap between class segments (stride > n)
     double mx = f[i];
     for (int c = 1; c < C; ++c) mx = fmax(mx, f[(int64_t)c * stride + i]);
     double s = 0.0;
     for (int c = 0; c < C; ++c) s += exp(f[(int64_t)c * stride + i] - mx);
-    for (int c = 0; c < C; ++c) pi[(int64_t)c * stride + i] = exp(f[(int64_t)c * stride + i] - mx) / s;
+    pi[k] = exp(f[cw * stride + i] - mx) / s;
 }
 
 // Reference-faithful multiclass Hessian pieces (GP_multi_classification.py:150-157).  The reference's
@@ -58,9 +64,9 @@ __global__ void softmax_classes_kernel(int C, int64_t n, int64_t stride, const d
 __global__ void __launch_bounds__(256) multi_ref_hessian_kernel(int C, int64_t n, int64_t stride, const double* __restrict__ Kinv,
                                                                int64_t ld, const double* __restrict__ pi_vec, double c_diag,
                                                                int64_t np_, double* __restrict__ out) {
-    const int64_t a = blockIdx.y;
+    const int64_t a = blockIdx.x;
     const int64_t N = (int64_t)C * n;
-    for (int64_t b = (int64_t)blockIdx.x * 256 + threadIdx.x; b < np_; b += (int64_t)gridDim.x * 256) {
+    for (int64_t b = (int64_t)blockIdx.y * 256 + threadIdx.x; b < np_; b += (int64_t)gridDim.y * 256) {
         double v;
         if (a < N && b < N) {
             v = Kinv[a * ld + b];
@@ -102,10 +108,10 @@ __global__ void multi_b_kernel(int C, int64_t n, const double* __restrict__ pi, 
 // is written when accumulate == 0 so that Esum stays factorable on the padded size.
 __global__ void __launch_bounds__(256) scale_sym_acc_kernel(const double* __restrict__ X, const double* __restrict__ sd, int64_t n,
                                                            int64_t np_, int64_t ld, int accumulate, double* __restrict__ E) {
-    const int64_t r = blockIdx.y;
+    const int64_t r = blockIdx.x;
     const double sr = r < n ? sd[r] : 0.0;
     const int64_t cend = ((r / GPX_T) + 1) * GPX_T;  // through the end of the diagonal tile
-    for (int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x; c < cend; c += (int64_t)gridDim.x * 256) {
+    for (int64_t c = (int64_t)blockIdx.y * 256 + threadIdx.x; c < cend; c += (int64_t)gridDim.y * 256) {
         double v;
         if (r < n && c < n) v = sr * X[r * ld + c] * sd[c];
         else v = (!accumulate && r == c) ? 1.0 : 0.0;
@@ -146,7 +152,7 @@ __global__ void __launch_bounds__(256) symv_lower_col_kernel(int64_t n, const do
 
 extern "C" int gpx_logistic_terms(gpx_handle h, int mode, int64_t n, const double* y, const double* f, double* grad,
                                   double* w, double* sw) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     GPX_REQUIRE(mode == 0 || mode == 1, 2);
     logistic_terms_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(mode, n, y, f, grad, w, sw);
     GPX_CHECK_LAUNCH(h);
@@ -154,26 +160,28 @@ extern "C" int gpx_logistic_terms(gpx_handle h, int mode, int64_t n, const doubl
 }
 
 extern "C" int gpx_build_B(gpx_handle h, const double* K, const double* sw, int64_t n, int64_t np_, int64_t ld, double* B) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     GPX_REQUIRE(np_ % GPX_T == 0 && np_ >= n, 5);
-    dim3 grid((unsigned)((np_ + 255) / 256 > 64 ? 64 : (np_ + 255) / 256), (unsigned)np_);
+    dim3 grid((unsigned)np_, (unsigned)((np_ + 255) / 256 > 64 ? 64 : (np_ + 255) / 256));
     build_B_kernel<<<grid, 256, 0, h->stream>>>(K, sw, n, np_, ld, B);
     GPX_CHECK_LAUNCH(h);
     return 0;
 }
 
 extern "C" int gpx_softmax_classes(gpx_handle h, int C, int64_t n, int64_t stride, const double* f, double* pi) {
-    GPX_REQUIRE(h != nullptr, 1);
-    softmax_classes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(C, n, stride, f, pi);
+    GPX_ENTER(h);
+    GPX_REQUIRE(C >= 1 && n >= 1 && stride >= 1, 2);
+    const int64_t outs = (int64_t)(C - 1) * stride + n;
+    softmax_classes_kernel<<<(unsigned)((outs + 255) / 256), 256, 0, h->stream>>>(C, n, stride, f, pi);
     GPX_CHECK_LAUNCH(h);
     return 0;
 }
 
 extern "C" int gpx_multi_ref_hessian(gpx_handle h, int C, int64_t n, int64_t stride, const double* Kinv, int64_t ld,
                                      const double* pi_vec, double c_diag, int64_t np_, double* out) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     GPX_REQUIRE(np_ % GPX_T == 0 && np_ >= (int64_t)C * n, 9);
-    dim3 grid((unsigned)((np_ + 255) / 256 > 64 ? 64 : (np_ + 255) / 256), (unsigned)np_);
+    dim3 grid((unsigned)np_, (unsigned)((np_ + 255) / 256 > 64 ? 64 : (np_ + 255) / 256));
     multi_ref_hessian_kernel<<<grid, 256, 0, h->stream>>>(C, n, stride, Kinv, ld, pi_vec, c_diag, np_, out);
     GPX_CHECK_LAUNCH(h);
     return 0;
@@ -181,14 +189,14 @@ extern "C" int gpx_multi_ref_hessian(gpx_handle h, int C, int64_t n, int64_t str
 
 extern "C" int gpx_multi_ref_wf(gpx_handle h, int C, int64_t n, int64_t stride, const double* pi_vec, const double* f,
                                 double* out) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     multi_ref_wf_kernel<<<(unsigned)(((int64_t)C * n + 255) / 256), 256, 0, h->stream>>>(C, n, stride, pi_vec, f, out);
     GPX_CHECK_LAUNCH(h);
     return 0;
 }
 
 extern "C" int gpx_multi_b(gpx_handle h, int C, int64_t n, const double* pi, const double* f, const double* y, double* b) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     multi_b_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(C, n, pi, f, y, b);
     GPX_CHECK_LAUNCH(h);
     return 0;
@@ -196,16 +204,16 @@ extern "C" int gpx_multi_b(gpx_handle h, int C, int64_t n, const double* pi, con
 
 extern "C" int gpx_scale_sym_acc(gpx_handle h, const double* X, const double* sd, int64_t n, int64_t np_, int64_t ld,
                                  int accumulate, double* E) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     GPX_REQUIRE(np_ % GPX_T == 0 && np_ >= n, 5);
-    dim3 grid((unsigned)((np_ + 255) / 256 > 64 ? 64 : (np_ + 255) / 256), (unsigned)np_);
+    dim3 grid((unsigned)np_, (unsigned)((np_ + 255) / 256 > 64 ? 64 : (np_ + 255) / 256));
     scale_sym_acc_kernel<<<grid, 256, 0, h->stream>>>(X, sd, n, np_, ld, accumulate, E);
     GPX_CHECK_LAUNCH(h);
     return 0;
 }
 
 extern "C" int gpx_symv_lower(gpx_handle h, int64_t n, const double* S, int64_t ld, const double* x, double* y) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     int64_t blocks = (n + 7) / 8;
     if (blocks > 148 * 16) blocks = 148 * 16;
     symv_lower_row_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(n, S, ld, x, y);
@@ -218,10 +226,10 @@ extern "C" int gpx_symv_lower(gpx_handle h, int64_t n, const double* S, int64_t 
 namespace {
 __global__ void __launch_bounds__(256) scale_rows_kernel(int64_t rows, int64_t cols, int64_t ld, const double* __restrict__ s,
                                                         double* __restrict__ M) {
-    const int64_t r = blockIdx.y;
+    const int64_t r = blockIdx.x;
     if (r >= rows) return;
     const double sr = s[r];
-    for (int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x; c < cols; c += (int64_t)gridDim.x * 256) M[r * ld + c] *= sr;
+    for (int64_t c = (int64_t)blockIdx.y * 256 + threadIdx.x; c < cols; c += (int64_t)gridDim.y * 256) M[r * ld + c] *= sr;
 }
 // mirror the strictly-lower triangle into the upper one (tile-wise transpose through shared memory)
 __global__ void __launch_bounds__(256) symmetrize_kernel(int64_t n, double* __restrict__ A, int64_t ld) {
@@ -242,16 +250,16 @@ __global__ void __launch_bounds__(256) symmetrize_kernel(int64_t n, double* __re
 }  // namespace
 
 extern "C" int gpx_scale_rows(gpx_handle h, int64_t rows, int64_t cols, int64_t ld, const double* s, double* M) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     if (rows <= 0 || cols <= 0) return 0;
-    dim3 grid((unsigned)((cols + 255) / 256 > 64 ? 64 : (cols + 255) / 256), (unsigned)rows);
+    dim3 grid((unsigned)rows, (unsigned)((cols + 255) / 256 > 64 ? 64 : (cols + 255) / 256));
     scale_rows_kernel<<<grid, 256, 0, h->stream>>>(rows, cols, ld, s, M);
     GPX_CHECK_LAUNCH(h);
     return 0;
 }
 
 extern "C" int gpx_symmetrize(gpx_handle h, int64_t n, double* A, int64_t ld) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     const unsigned nb = (unsigned)((n + 31) / 32);
     symmetrize_kernel<<<dim3(nb, nb), 256, 0, h->stream>>>(n, A, ld);
     GPX_CHECK_LAUNCH(h);

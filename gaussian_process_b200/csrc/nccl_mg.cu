@@ -271,7 +271,7 @@ extern "C" int gpx_nccl_unique_id(void* id128) {
 }
 
 extern "C" int gpx_nccl_init(gpx_handle h, const void* id128, int rank, int world) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     GPX_TRY(nccl_load(nullptr));
     ncclUniqueId_t id;
     memcpy(&id, id128, sizeof(id));
@@ -288,7 +288,7 @@ extern "C" int gpx_nccl_init(gpx_handle h, const void* id128, int rank, int worl
 extern "C" int gpx_mg_fit_grad(gpx_handle h, int kind, const double* X, int64_t n, int D, const double* theta_host, int ntheta,
                                double s, const double* y, int nb, double* ws, double* alpha, double* out3, double* grad,
                                int with_grad) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     GPX_REQUIRE(nb >= GPX_T && nb % GPX_T == 0, 10);
     const int P = h->world, p = h->rank;
     GPX_REQUIRE(P == 1 || h->nccl_comm != nullptr, 1);
@@ -454,7 +454,7 @@ extern "C" int gpx_mg_fit_grad(gpx_handle h, int kind, const double* X, int64_t 
 extern "C" int gpx_mg_emulate_fit_grad(gpx_handle h, int P, int kind, const double* X, int64_t n, int D,
                                        const double* theta_host, int ntheta, double s, const double* y, int nb, double* ws_all,
                                        double* alpha, double* out3, double* grad) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     GPX_REQUIRE(P >= 1 && P <= 16, 2);
     cudaStream_t S = h->stream;
     std::vector<MgRank> R(P);

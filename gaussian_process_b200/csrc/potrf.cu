@@ -287,7 +287,8 @@ __global__ void zero_upper_tiles_kernel(double* A, int64_t lda, int nt) {
 
 int leaf(gpx_ctx* h, double* A, int64_t lda, double* dinv_tile, int goff, int batch = 1, int64_t strideA = 0,
          int64_t strideD = 0) {
-    static bool configured = false;
+    static bool configured_dev[GPX_MAX_DEVICES] = {};
+    bool& configured = configured_dev[h->device % GPX_MAX_DEVICES];   // cudaFuncSetAttribute is per device
     if (!configured) {
         GPX_CUDA(cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM));
         configured = true;
@@ -626,7 +627,7 @@ int la_threshold() {   // largest n factored by the look-ahead algorithm (0 disa
 }  // namespace
 
 extern "C" int gpx_potrf_async(gpx_handle h, double* A, int64_t n, int64_t lda, double* dinv) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     GPX_REQUIRE(A != nullptr && ((uintptr_t)A % 16) == 0, 2);
     GPX_REQUIRE(n > 0 && n % LT == 0, 3);
     GPX_REQUIRE(lda >= n && lda % 2 == 0, 4);
@@ -641,7 +642,7 @@ extern "C" int gpx_potrf_async(gpx_handle h, double* A, int64_t n, int64_t lda, 
 }
 
 extern "C" int gpx_potrf(gpx_handle h, double* A, int64_t n, int64_t lda, double* dinv) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     GPX_CUDA(cudaMemsetAsync(h->d_info, 0, sizeof(int), h->stream));
     int r = gpx_potrf_async(h, A, n, lda, dinv);
     if (r != 0) return r;
@@ -652,7 +653,8 @@ extern "C" int gpx_potrf(gpx_handle h, double* A, int64_t n, int64_t lda, double
 }
 
 extern "C" int gpx_potrf_info(gpx_handle h, int* info_out) {
-    GPX_REQUIRE(h != nullptr && info_out != nullptr, 1);
+    GPX_ENTER(h);
+    GPX_REQUIRE(info_out != nullptr, 2);
     int info = 0;
     GPX_TRY(gpx_read_info(h, &info));
     GPX_CUDA(cudaMemsetAsync(h->d_info, 0, sizeof(int), h->stream));   // read-and-clear: the flag is sticky across async calls
@@ -663,7 +665,7 @@ extern "C" int gpx_potrf_info(gpx_handle h, int* info_out) {
 
 extern "C" int gpx_trsm(gpx_handle h, const double* L, int64_t n, int64_t ldl, const double* dinv, int trans,
                         double* B, int64_t nrhs, int64_t ldb) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     GPX_REQUIRE(n > 0 && n % LT == 0, 3);
     GPX_REQUIRE(nrhs > 0 && nrhs % LT == 0, 8);
     return trsm_left(h, L, n, ldl, dinv, trans, B, nrhs, ldb);
@@ -750,7 +752,7 @@ int trtri_levels(gpx_ctx* h, double* A, int64_t n, int64_t lda, const double* di
 }  // namespace
 
 extern "C" int gpx_trtri(gpx_handle h, double* L, int64_t n, int64_t ldl, const double* dinv, double* work) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     GPX_REQUIRE(n > 0 && n % LT == 0, 3);
     GPX_REQUIRE(n == LT || work != nullptr, 6);
     const int64_t nt = n / LT;
@@ -759,7 +761,7 @@ extern "C" int gpx_trtri(gpx_handle h, double* L, int64_t n, int64_t ldl, const 
 }
 
 extern "C" int gpx_lauum(gpx_handle h, const double* Linv, int64_t n, int64_t ldl, double* out, int64_t ldo) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     GPX_REQUIRE(n > 0 && n % LT == 0, 3);
     GPX_REQUIRE(out != Linv, 5);
     GemmArgs a = base_args();  // out[i][j] = sum_{k >= i} Linv[k][i] Linv[k][j], i >= j
@@ -855,7 +857,7 @@ extern "C" int gpx_block_size_for(int64_t n) {
 // D: (n/bs) blocks of bs x bs doubles; work: n*bs/4 doubles.
 extern "C" int gpx_block_inverses(gpx_handle h, const double* L, int64_t n, int64_t ldl, const double* dinv, int bs, double* D,
                                   double* work) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     GPX_REQUIRE(n > 0 && n % bs == 0 && bs >= LT && bs % LT == 0 && (bs & (bs - 1)) == 0, 6);
     const int nB = (int)(n / bs);
     GPX_CUDA(cudaMemsetAsync(D, 0, (size_t)n * bs * sizeof(double), h->stream));
@@ -952,14 +954,14 @@ int trsm_big_rec(gpx_ctx* h, const double* L, int64_t n, int64_t ldl, const doub
 
 extern "C" int gpx_trsv_big(gpx_handle h, const double* L, int64_t n, int64_t ldl, const double* D, int bs, int trans, double* x,
                             double* tmp) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     GPX_REQUIRE(n > 0 && n % bs == 0, 3);
     return trsv_big_rec(h, L, n, ldl, D, bs, trans, x, tmp);
 }
 
 extern "C" int gpx_trsm_big(gpx_handle h, const double* L, int64_t n, int64_t ldl, const double* D, int bs, int trans, double* B,
                             int64_t nrhs, int64_t ldb, double* tmp) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     GPX_REQUIRE(n > 0 && n % bs == 0, 3);
     GPX_REQUIRE(nrhs > 0 && nrhs % LT == 0, 9);
     return trsm_big_rec(h, L, n, ldl, D, bs, trans, B, nrhs, ldb, tmp);

@@ -460,7 +460,8 @@ int ensure_pinned(gpx_ctx* h, size_t bytes) {
 template <int KIND>
 int launch_small(gpx_ctx* h, const CovParams& p, int N, int n, int nf, int mode, double s, double jitter, const double* in,
                  double* out, double* keep, size_t smem) {
-    static bool configured = false;
+    static bool configured_dev[GPX_MAX_DEVICES] = {};
+    bool& configured = configured_dev[h->device % GPX_MAX_DEVICES];   // cudaFuncSetAttribute is per device
     if (!configured) {
         GPX_CUDA(cudaFuncSetAttribute(gp_small_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
@@ -474,7 +475,7 @@ int launch_small(gpx_ctx* h, const CovParams& p, int N, int n, int nf, int mode,
 int small_run(gpx_ctx* h, int kind, const double* X, int64_t N, int D, const double* y, const double* Xs, int64_t n,
               const double* theta, int ntheta, double s, double jitter, const double* Z, int nf, int mode, double* mu,
               double* var, double* fpost, double* lml) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     GPX_REQUIRE(kind >= 0 && kind <= 3, 2);
     GPX_REQUIRE(N >= 1 && N <= SMAX, 4);
     GPX_REQUIRE(D >= 1, 5);
@@ -551,7 +552,7 @@ extern "C" int gpx_gp_small_fit_host(gpx_handle h, int kind, const double* X, in
 }
 
 extern "C" int gpx_gp_small_sample_host(gpx_handle h, int64_t n, int nf, const double* Z, double* fpost) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     GPX_REQUIRE(n >= 1 && n == h->small_n, 2);      // the factor of the last successful gpx_gp_small_fit_host
     GPX_REQUIRE(nf >= 1 && Z && fpost, 3);
     const size_t nZ = (size_t)n * nf;
@@ -576,7 +577,8 @@ namespace {
 template <int KIND>
 int launch_small_grad(gpx_ctx* h, const CovParams& p, int N, double s, int want_grad, int ascent, double step, double tol,
                       int max_iter, const double* in, double* out, size_t smem) {
-    static bool configured = false;
+    static bool configured_dev[GPX_MAX_DEVICES] = {};
+    bool& configured = configured_dev[h->device % GPX_MAX_DEVICES];   // cudaFuncSetAttribute is per device
     if (!configured) {
         GPX_CUDA(cudaFuncSetAttribute(gp_small_grad_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
@@ -588,7 +590,7 @@ int launch_small_grad(gpx_ctx* h, const CovParams& p, int N, double s, int want_
 
 int small_grad_run(gpx_ctx* h, int kind, const double* X, int64_t N, int D, const double* y, const double* theta, int ntheta,
                    double s, int want_grad, int ascent, double step, double tol, int max_iter, double* out19) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     GPX_REQUIRE(kind >= 0 && kind <= 3, 2);
     GPX_REQUIRE(N >= 1 && N <= SMAX, 4);
     GPX_REQUIRE(D >= 1, 5);
@@ -662,7 +664,8 @@ extern "C" int gpx_gp_small_ascent_host(gpx_handle h, const double* X, int64_t N
 namespace {
 template <int KIND>
 int launch_small_prior(gpx_ctx* h, const CovParams& p, int n, double s, const double* Xs, double* keep, double* out, size_t smem) {
-    static bool configured = false;
+    static bool configured_dev[GPX_MAX_DEVICES] = {};
+    bool& configured = configured_dev[h->device % GPX_MAX_DEVICES];   // cudaFuncSetAttribute is per device
     if (!configured) {
         GPX_CUDA(cudaFuncSetAttribute(gp_small_prior_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
@@ -675,7 +678,7 @@ int launch_small_prior(gpx_ctx* h, const CovParams& p, int n, double s, const do
 
 extern "C" int gpx_gp_small_prior_factor_host(gpx_handle h, int kind, const double* Xs, int64_t n, int D, const double* theta,
                                               int ntheta, double s) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     GPX_REQUIRE(kind >= 0 && kind <= 3, 2);
     GPX_REQUIRE(Xs != nullptr && theta != nullptr, 3);
     GPX_REQUIRE(n >= 1 && n <= SMAX, 4);

@@ -67,7 +67,7 @@ void gpx_phase_mark(gpx_ctx* h, int phase) {
 }
 
 extern "C" int gpx_timing_enable(gpx_handle h, int on) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     if (!h->timing) h->timing = new gpx_timing();
     gpx_timing* t = (gpx_timing*)h->timing;
     t->used = 0;

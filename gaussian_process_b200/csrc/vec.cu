@@ -192,8 +192,8 @@ __global__ void moments_finish_kernel(int64_t m, int nparts, const double* __res
 //  0: out = a*x            1: out = x + a*y         2: out = x*y (+ z if z)     3: out = x - y*z
 //  4: out = a (fill)       5: out = x*y + z         6: out = (x - y)            7: out = x*y - z
 //  8: out = -log(1 + exp(-x))  (GP_binary...:63)     9: out = 1/(1+exp(-x)) (expit)   10: out = sqrt(x)
-__global__ void vec_op_kernel(int op, int64_t n, double a, const double* __restrict__ x, const double* __restrict__ y,
-                              const double* __restrict__ z, double* __restrict__ out) {
+// `out` may alias x, y or z (each thread reads and writes only its own index), hence no __restrict__.
+__global__ void vec_op_kernel(int op, int64_t n, double a, const double* x, const double* y, const double* z, double* out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double r = 0.0;
@@ -284,18 +284,18 @@ int trsv_rec(gpx_ctx* h, const double* L, int64_t n, int64_t ldl, const double* 
 
 extern "C" int gpx_gemv(gpx_handle h, int trans, int64_t m, int64_t n, double alpha, const double* A, int64_t lda,
                         const double* x, double beta, double* y) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     return gemv_impl(h, trans, m, n, alpha, A, lda, x, beta, y);
 }
 
 extern "C" int gpx_trsv(gpx_handle h, const double* L, int64_t n, int64_t ldl, const double* dinv, int trans, double* x) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     GPX_REQUIRE(n > 0 && n % LT == 0, 3);
     return trsv_rec(h, L, n, ldl, dinv, trans, x);
 }
 
 extern "C" int gpx_dot(gpx_handle h, int64_t n, const double* x, const double* y, double* out) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     int blocks = (int)((n + 255) / 256);
     if (blocks > 592) blocks = 592;
     if (blocks < 1) blocks = 1;
@@ -309,7 +309,7 @@ extern "C" int gpx_dot(gpx_handle h, int64_t n, const double* x, const double* y
 
 extern "C" int gpx_lml(gpx_handle h, const double* L, int64_t n, int64_t ldl, const double* y, const double* alpha,
                        double* out3) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     int blocks = (int)((n + 255) / 256);
     if (blocks > 592) blocks = 592;
     GPX_TRY(ensure_partial(h, 2048));
@@ -324,7 +324,7 @@ extern "C" int gpx_lml(gpx_handle h, const double* L, int64_t n, int64_t ldl, co
 
 extern "C" int gpx_predict_moments(gpx_handle h, const double* Ks, const double* V, int64_t n, int64_t m, int64_t ld,
                                    const double* alpha, const double* kss_diag, double* mu, double* var) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     const int64_t colblocks = (m + 127) / 128;
     int64_t nparts = (148 * 4 + colblocks - 1) / colblocks;
     int64_t max_parts = (n + 63) / 64;
@@ -345,7 +345,7 @@ extern "C" int gpx_predict_moments(gpx_handle h, const double* Ks, const double*
 
 extern "C" int gpx_vec_op(gpx_handle h, int op, int64_t n, double a, const double* x, const double* y, const double* z,
                           double* out) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     if (n <= 0) return 0;
     vec_op_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(op, n, a, x, y, z, out);
     GPX_CHECK_LAUNCH(h);
@@ -353,7 +353,7 @@ extern "C" int gpx_vec_op(gpx_handle h, int op, int64_t n, double a, const doubl
 }
 
 extern "C" int gpx_copy_strided(gpx_handle h, int64_t n, const double* src, int64_t src_stride, double* dst, int64_t dst_stride) {
-    GPX_REQUIRE(h != nullptr, 1);
+    GPX_ENTER(h);
     if (n <= 0) return 0;
     copy_strided_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(n, src, src_stride, dst, dst_stride);
     GPX_CHECK_LAUNCH(h);

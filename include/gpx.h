@@ -77,6 +77,13 @@ int gpx_cov_build(gpx_handle h, int kind, const double* X1, int64_t n1, const do
                   int D, const double* theta_host, int ntheta, double diag_add, int flags,
                   double* K, int64_t n1p, int64_t n2p, int64_t ldk, double* dK, int64_t dk_stride);
 
+/* One additive term of the CO2 composite as an element-wise map of a precomputed squared-distance matrix: replaces
+ * kernel_1 .. kernel_4 (CO2_example.py:9-66), which take `sqdist` (and kernel_2 also `l2_norm`, NULL = sqrt(sqdist)).
+ * term 1: t0^2 exp(-.5 d/t1^2); 2: t0^2 exp(-.5 d/t1^2 - 2 (sin(pi r)/t2)^2); 3: t0^2 (1 + .5 d/(t2 t1^2))^-t2;
+ * 4: t0^2 exp(-.5 d/t1^2) + t2^2 [i == j] when rows == cols (the reference tests the shape only, :60).  Device pointers. */
+int gpx_co2_term(gpx_handle h, int term, int64_t rows, int64_t cols, const double* sqdist, int64_t ldd,
+                 const double* l2_norm, int64_t ldr, double t0, double t1, double t2, double* out, int64_t ldo);
+
 /* ---- A4: Cholesky (np.linalg.cholesky call sites) ------------------------
  * In-place lower Cholesky of the n x n (n % 128 == 0) matrix A; on return the lower triangle holds
  * L and the strict upper triangle is zero (NumPy convention).  Blocked recursive right-looking:

@@ -43,8 +43,53 @@ def _quiet(fn, *a, **k):
     return out, buf.getvalue()
 
 
+def ka6_co2_bo() -> None:
+    """KA6: the CO2 Bayesian-optimisation driver end to end (CO2_example.py:330-379) on a 60-point Mauna-Loa-shaped
+    series: 4 acquisition labels x 10 iterations x 500 candidates, `random` and NumPy RNGs seeded.  Stores the returned
+    theta, every printed per-iteration best LML and the book LML."""
+    import random
+    R = load_reference()
+    C2 = R["CO2_example"]
+
+    # The driver predates NumPy 2 / Python 3 in two library calls (np.delete with an EMPTY float index array from
+    # overlap(), random.sample on an ndarray).  The reference file stays untouched; its module namespace gets proxies
+    # that restore the old library semantics for exactly those two calls.
+    class _NpCompat:
+        def __getattr__(self, k):
+            return getattr(np, k)
+
+        @staticmethod
+        def delete(arr, obj, axis=None):
+            obj = np.asarray(obj)
+            if obj.dtype.kind == "f":
+                obj = obj.astype(np.int64)
+            return np.delete(arr, obj, axis)
+
+    class _RandomCompat:
+        def __getattr__(self, k):
+            return getattr(random, k)
+
+        @staticmethod
+        def sample(pop, k):
+            return random.sample(list(pop), k)
+
+    C2.np, C2.random = _NpCompat(), _RandomCompat()
+    X, y, Xs = O.synth_c2(60, 24)
+    random.seed(42)
+    np.random.seed(42)
+    th, txt = _quiet(C2.tune_hyperparameters_BO, X, Xs, y)
+    lines = txt.splitlines()
+    best = [float(lines[i + 1]) for i, ln in enumerate(lines) if ln.endswith("th iteration!")]
+    book = float(lines[-1])
+    np.savez(os.path.join(GOLD, "ka6_co2_bo.npz"), N=60, theta=np.asarray(th), best_lml=np.array(best), book_lml=np.float64(book),
+             nlines=len(lines))
+    print("ka6: theta", th, "best", best[-3:], "book", book)
+
+
 def main() -> None:
     os.makedirs(GOLD, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "ka6":
+        return ka6_co2_bo()
     R = load_reference()
     G, T, C2 = R["GP_regression"], R["tune_hyperparms_regression"], R["CO2_example"]
     B, M = R["GP_binary_classification"], R["GP_multi_classification"]
@@ -162,6 +207,7 @@ def main() -> None:
                             pi_probe=pv, pim_probe=pm)
     finally:
         os.chdir(cwd)
+    ka6_co2_bo()
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
 
