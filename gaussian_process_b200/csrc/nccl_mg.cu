@@ -250,6 +250,13 @@ int init_rank(MgRank& r, gpx_ctx* h, int P, int p, int64_t n, int nb, double* ws
 
 }  // namespace
 
+// sum over the ranks of the handle's communicator, in place, on the handle's stream (no-op for a single rank)
+int gpx_nccl_allreduce_sum(gpx_ctx* h, double* buf, size_t count) {
+    if (h->world <= 1 || h->nccl_comm == nullptr) return 0;
+    GPX_NCCL(g_nccl.AllReduce(buf, buf, count, NCCL_F64, NCCL_SUM, (ncclComm_p)h->nccl_comm, h->stream));
+    return 0;
+}
+
 extern "C" int64_t gpx_mg_padded_dim(int64_t n, int nb, int world) {
     const int64_t unit = (int64_t)nb * world;
     return ((n + unit - 1) / unit) * unit;

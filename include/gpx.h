@@ -187,6 +187,34 @@ int gpx_copy_strided(gpx_handle h, int64_t n, const double* src, int64_t src_str
 /* out[0] = sum_i x_i*y_i (y may equal x) -- device scalar */
 int gpx_dot(gpx_handle h, int64_t n, const double* x, const double* y, double* out);
 
+/* ---- A10/A11: device-resident Laplace iterations (one call = build B -> factor -> solves -> f update -> error; caller
+ * workspace, no allocation, no host synchronisation inside a step) -------------------------------------------------------*/
+int64_t gpx_laplace_binary_ws_elems(int64_t np_);
+/* One textbook Newton iteration of GP_binary_classification.py:104-111 (W and gradient at the current f; R&W Alg. 3.1).
+ * K: np x np full symmetric covariance; y, f, f_new: np doubles (zero padded), f_new != f; B (np x np) receives
+ * chol(I + W^1/2 K W^1/2), dinv its leaf inverses; ws: gpx_laplace_binary_ws_elems(np) doubles, on return ws[0..np) =
+ * gradient, ws[np..2np) = W, ws[2np..3np) = W^1/2 of this iteration; err_dev[0] = |f_new - f|_2 (device).  A failed
+ * pivot is reported by gpx_potrf_info. */
+int gpx_laplace_binary_step(gpx_handle h, const double* K, int64_t n, int64_t np_, int64_t ld, const double* y,
+                            const double* f, double* B, double* dinv, double* ws, double* f_new, double* err_dev);
+/* The whole as-shipped loop of GP_binary_classification.py:86-133: W and the gradient are evaluated at f_prior (never at
+ * f), B is factored once, inv(L) is formed explicitly (:108) and applied as two mat-vecs, iteration stops at
+ * |f_new - f| <= tol.  Linv (np x np) receives inv(L); g_out / w_out / sw_out / f_out: np doubles (device);
+ * errors_host[max_iter] and *iters_out are HOST memory.  Returns > 0 when B is not positive definite. */
+int gpx_laplace_binary_ref_fit(gpx_handle h, const double* K, int64_t n, int64_t np_, int64_t ld, const double* y,
+                               const double* f_prior, double tol, int max_iter, double* B, double* dinv, double* Linv,
+                               double* ws, double* f_out, double* g_out, double* w_out, double* sw_out,
+                               double* errors_host, int* iters_out);
+int64_t gpx_laplace_multi_ws_elems(int64_t np_, int C, int nlanes);
+/* One textbook multiclass iteration (GP_multi_classification.py:66-126 / R&W Alg. 3.3) over the nloc classes
+ * classes[0..nloc) (HOST ints) owned by this rank.  K: np x np shared covariance block; y, f, f_new, pi: C x n class-major;
+ * Linv_store: nloc x np x np (receives L_c^-1); lanes[nlanes]: HOST array of handles, each bound to its own stream, through
+ * which the independent per-class factorisations (:88-101) are issued; sums over classes (sum_c E_c, R^T c, f) are
+ * all-reduced over h's NCCL communicator when it has one.  err_dev[0] = |f_new - f|_2.  No host synchronisation. */
+int gpx_laplace_multi_step(gpx_handle h, const gpx_handle* lanes, int nlanes, const double* K, int64_t n, int64_t np_,
+                           int64_t ld, int C, const int* classes, int nloc, const double* y, const double* f, double* ws,
+                           double* Linv_store, double* f_new, double* pi, double* err_dev);
+
 /* ---- measurement helpers --------------------------------------------------------------------
  * register-resident DMMA.8x8x4 / DFMA issue-rate microbenchmarks -> measured FP64 peaks (TFLOP/s). */
 int gpx_bench_fp64_peak(gpx_handle h, int use_dmma, int iters, double* tflops_out, double* ms_out);
