@@ -37,7 +37,8 @@ def multiclass_newton_sharded(eng: Engine, Ksub_dev, y, C: int, n: int, toleranc
     """Textbook softmax Laplace with class c on rank c mod P: per-class B_c factorisations and E_c stay local,
     sum_c E_c (n x n), R^T c (n) and f (C x n) are all-reduced.  Returns the fitted MultiLaplaceNewton."""
     world, rank = _world_rank()
-    model = MultiLaplaceNewton(eng, Ksub_dev, C, n, classes=P.shard_classes(C, rank, world),
-                               allreduce=(P.allreduce_sum_ if world > 1 else None))
+    if world > 1:
+        eng.mg_init()          # libgpx's own NCCL communicator: the step all-reduces sum_c E_c, R^T c and f inside the call
+    model = MultiLaplaceNewton(eng, Ksub_dev, C, n, classes=P.shard_classes(C, rank, world))
     model.fit(y, tolerance, max_iter)
     return model

@@ -73,40 +73,62 @@ class BinaryLaplace:
         return f_new, a, err
 
     # -- reference-faithful ------------------------------------------------------------------------
+    def _workspace(self):
+        if getattr(self, "_ws", None) is None:
+            eng = self.eng
+            self._ws = eng.empty(int(eng.lib.gpx_laplace_binary_ws_elems(self.npad)))
+            self._B = eng.empty(self.npad, self.npad)
+            self._dinv = eng.empty(self.npad // GPX_TILE, GPX_TILE, GPX_TILE)
+            self._err = eng.empty(2)
+        return self._ws
+
     def fit_reference(self, y, f_prior, tolerance: float = 1e-4, max_iter: int = 10000, on_iter=None):
         """W, gradient evaluated at ``f_prior`` every iteration (never at f): B is factored once and the
-        iterate converges linearly.  Returns the number of iterations."""
+        iterate converges linearly.  The whole loop is ONE libgpx call (gpx_laplace_binary_ref_fit).
+        Returns the number of iterations."""
         eng = self.eng
         yd = self._pad_vec(y)
         fp = self._pad_vec(f_prior)
-        self.g, self.w, self.sw = self._terms(0, yd, fp)
-        self.L, self.dinv = self._factor_B(self.sw)
-        Linv = self.L.clone()                      # the reference forms inv(L) explicitly (:108) and returns it
-        eng.trtri(Linv, self.dinv)
-        self._Linv_full = Linv
-        f = eng.zeros(self.npad)
-        self.errors = []
-        for i in range(max_iter):
-            f, _, err = self._newton_step(f, self.g, self.w, self.sw, self.L, self.dinv, Linv)
-            self.errors.append(err)
-            if on_iter is not None:
-                on_iter(i, err)
-            if err <= tolerance:
-                break
-        self.f = f
+        ws = self._workspace()
+        Linv = eng.empty(self.npad, self.npad)
+        self.g, self.w, self.sw, f = eng.empty(self.npad), eng.empty(self.npad), eng.empty(self.npad), eng.empty(self.npad)
+        errs = np.zeros(max_iter)
+        iters = ctypes.c_int(0)
+        eng._sync_stream()
+        _chk(eng, eng.lib.gpx_laplace_binary_ref_fit(
+            eng.h, eng._p(self.K), self.n, self.npad, self.K.stride(0), eng._p(yd), eng._p(fp), float(tolerance), int(max_iter),
+            eng._p(self._B), eng._p(self._dinv), eng._p(Linv), eng._p(ws), eng._p(f), eng._p(self.g), eng._p(self.w),
+            eng._p(self.sw), ctypes.c_void_p(errs.ctypes.data), ctypes.byref(iters)), "gpx_laplace_binary_ref_fit")
+        self.L, self.dinv, self._Linv_full, self.f = self._B, self._dinv, Linv, f
+        self.errors = [float(e) for e in errs[:iters.value]]
+        if on_iter is not None:
+            for i, e in enumerate(self.errors):
+                on_iter(i, e)
         return len(self.errors)
 
     # -- textbook Newton (R&W Alg 3.1) -----------------------------------------------------------
+    def newton_step(self, yd, f, f_new):
+        """One device-resident Newton iteration (gpx_laplace_binary_step): enqueues only, no allocation, no sync."""
+        eng = self.eng
+        ws = self._workspace()
+        _chk(eng, eng.lib.gpx_laplace_binary_step(eng.h, eng._p(self.K), self.n, self.npad, self.K.stride(0), eng._p(yd),
+                                                  eng._p(f), eng._p(self._B), eng._p(self._dinv), eng._p(ws), eng._p(f_new),
+                                                  eng._p(self._err)), "gpx_laplace_binary_step")
+
     def fit_newton(self, y, f0=None, tolerance: float = 1e-10, max_iter: int = 100, on_iter=None):
         eng = self.eng
         yd = self._pad_vec(y)
         f = eng.zeros(self.npad) if f0 is None else self._pad_vec(f0)
+        f_new = eng.zeros(self.npad)
+        self._workspace()
         self.errors = []
         for i in range(max_iter):
-            g, w, sw = self._terms(1, yd, f)
-            L, dinv = self._factor_B(sw)
-            f, _, err = self._newton_step(f, g, w, sw, L, dinv)
+            eng._sync_stream()
+            self.newton_step(yd, f, f_new)
+            err = float(self._err[0].item())             # the one read-back of the iteration (convergence decision)
+            eng.potrf_check()
             self.errors.append(err)
+            f, f_new = f_new, f
             if on_iter is not None:
                 on_iter(i, err)
             if err <= tolerance:
@@ -221,138 +243,78 @@ class MultiLaplaceReference:
 class MultiLaplaceNewton:
     """Textbook multiclass Laplace (R&W Alg. 3.3) with one shared n x n covariance block ``Ksub`` --
     the structure of the reference's block_diag(K_sub x C) (GP_multi...:233-238).  Classes may be sharded
-    across ranks: ``classes`` lists the classes this process owns; sums over classes are completed by
-    ``allreduce`` (a callable on device tensors) when given."""
+    across ranks: ``classes`` lists the classes this process owns; sums over classes (sum_c E_c, R^T c, f) are
+    all-reduced inside libgpx over the engine's NCCL communicator (``Engine.mg_init()``) when the world has > 1 rank.
+    One iteration is ONE C-ABI call (``gpx_laplace_multi_step``) on a workspace allocated once."""
 
     def __init__(self, eng: Engine, Ksub, C: int, n: int, classes: Optional[List[int]] = None, allreduce=None,
                  concurrency: int = 4):
         self.eng, self.K, self.C, self.n, self.npad = eng, Ksub, int(C), int(n), Ksub.shape[0]
         self.classes = list(range(C)) if classes is None else list(classes)
-        self.allreduce = allreduce
         self.errors: List[float] = []
         self.f = self.pi = None
         # the per-class factorisations are independent: issue them through `concurrency` handles / CUDA streams so the
         # latency-bound parts of one class overlap with the DMMA-bound parts of another
         self.nstreams = max(1, min(int(concurrency), len(self.classes)))
         self._lanes = None
+        self.allreduce = allreduce   # kept for API compatibility: libgpx all-reduces over its own communicator
 
     def _make_lanes(self):
         from .engine import new_engine
-        eng, npad = self.eng, self.npad
+        eng = self.eng
         T = eng.torch
         lanes = []
         for k in range(self.nstreams):
             st = T.cuda.Stream(device=eng.device)
             with T.cuda.stream(st):
-                e = eng if self.nstreams == 1 else new_engine(eng.device.index)
-                lanes.append(dict(eng=e, stream=st, Ec=e.empty(npad, npad), work=e.empty(npad, npad), Esum=e.empty(npad, npad)))
+                e = new_engine(eng.device.index)      # own handle: own helper streams, scratch and pivot flag
+                e._sync_stream()
+                lanes.append(dict(eng=e, stream=st))
         return lanes
 
+    def _prepare(self):
+        if self._lanes is None:
+            eng, npad = self.eng, self.npad
+            self._lanes = self._make_lanes()
+            nl = len(self._lanes)
+            self._lane_arr = (ctypes.c_void_p * nl)(*[ln["eng"].h for ln in self._lanes])
+            self._ws = eng.empty(int(eng.lib.gpx_laplace_multi_ws_elems(npad, self.C, nl)))
+            self._Linv = eng.empty(max(1, len(self.classes)), npad, npad)
+            self._cls = (ctypes.c_int * max(1, len(self.classes)))(*self.classes)
+            self._err = eng.empty(2)
+
+    def step(self, yd, f, f_new, pi):
+        """One device-resident Alg-3.3 iteration (gpx_laplace_multi_step): enqueues only."""
+        eng = self.eng
+        _chk(eng, eng.lib.gpx_laplace_multi_step(
+            eng.h, self._lane_arr, len(self._lanes), eng._p(self.K), self.n, self.npad, self.K.stride(0), self.C, self._cls,
+            len(self.classes), eng._p(yd), eng._p(f), eng._p(self._ws), eng._p(self._Linv), eng._p(f_new), eng._p(pi),
+            eng._p(self._err)), "gpx_laplace_multi_step")
+
     def fit(self, y, tolerance: float = 1e-8, max_iter: int = 100, on_iter=None):
-        eng, C, n, npad = self.eng, self.C, self.n, self.npad
-        lib = eng.lib
-        T = eng.torch
+        eng, C, n = self.eng, self.C, self.n
         yd = eng.to_device(np.asarray(y, dtype=np.float64).reshape(C, n)) if not hasattr(y, "data_ptr") else y.reshape(C, n)
         yd = yd.contiguous()
-        f = eng.zeros(C, n)
-        pi = eng.zeros(C, n)
-        Linv = {c: eng.empty(npad, npad) for c in self.classes}
-        sd = {c: eng.zeros(npad) for c in self.classes}
-        if self._lanes is None:
-            self._lanes = self._make_lanes()
-        lanes = self._lanes
-        Esum = lanes[0]["Esum"]
-        main = T.cuda.current_stream(eng.device)
+        f, f_new, pi = eng.zeros(C, n), eng.zeros(C, n), eng.zeros(C, n)
+        self._prepare()
         self.errors = []
         for it in range(max_iter):
             eng._sync_stream()
-            _chk(eng, lib.gpx_softmax_classes(eng.h, C, n, n, eng._p(f), eng._p(pi)), "gpx_softmax_classes")
-            ready = T.cuda.Event()
-            ready.record(main)
-            used = [False] * len(lanes)
-            for idx, c in enumerate(self.classes):
-                lane = lanes[idx % len(lanes)]
-                e = lane["eng"]
-                with T.cuda.stream(lane["stream"]):
-                    if not used[idx % len(lanes)]:
-                        lane["stream"].wait_event(ready)
-                    e.vec_op(10, n, sd[c], x=pi[c])                          # D_c^1/2
-                    B = Linv[c]
-                    e._sync_stream()
-                    _chk(e, lib.gpx_build_B(e.h, e._p(self.K), e._p(sd[c]), n, npad, B.stride(0), e._p(B)), "gpx_build_B")
-                    dinv = e.potrf_async(B)                                  # :93  L_c
-                    e.trtri(B, dinv, lane["work"])                           # :94  L_c^-1 (kept for E_c matvecs)
-                    e.lauum(B, lane["Ec"])                                   # B_c^-1 (lower)
-                    _chk(e, lib.gpx_scale_sym_acc(e.h, e._p(lane["Ec"]), e._p(sd[c]), n, npad, lane["Esum"].stride(0),
-                                                  1 if used[idx % len(lanes)] else 0, e._p(lane["Esum"])), "gpx_scale_sym_acc")   # :95,:101
-                    used[idx % len(lanes)] = True
-            for k, lane in enumerate(lanes):                                 # join: pivot status + stream order
-                if used[k]:
-                    with T.cuda.stream(lane["stream"]):
-                        lane["eng"].potrf_check()
-                    done = T.cuda.Event()
-                    done.record(lane["stream"])
-                    main.wait_event(done)
-            eng._sync_stream()
-            if not any(used):  # this rank owns no class
-                Esum.zero_()
-            for k in range(1, len(lanes)):
-                if used[k]:
-                    eng.vec_op(1, npad * npad, Esum, a=1.0, x=Esum, y=lanes[k]["Esum"])
-            if self.allreduce is not None:
-                self.allreduce(Esum)
-            M = Esum                                                       # factored in place, rebuilt next iteration
-            dinvM = self._factor_padded(M)                                 # :107
-            b = eng.zeros(C, n)
-            _chk(eng, lib.gpx_multi_b(eng.h, C, n, eng._p(pi), eng._p(f), eng._p(yd), eng._p(b)), "gpx_multi_b")  # :113
-            cv = eng.zeros(C, npad)
-            rsum = eng.zeros(npad)
-            for c in self.classes:
-                kb = eng.gemv(self.K, b[c], eng.zeros(npad), m=n, n=n)
-                self._apply_E(c, Linv[c], sd[c], kb, cv[c])                # :114  c = E K b
-                eng.vec_op(1, n, rsum, a=1.0, x=rsum, y=cv[c])             # R^T c
-            if self.allreduce is not None:
-                self.allreduce(rsum)
-            eng.potrs_vec(M, dinvM, rsum)                                  # M^-T M^-1 R^T c
-            a = eng.zeros(C, n)
-            f_new = eng.zeros(C, n)
-            for c in self.classes:
-                ez = eng.zeros(npad)
-                self._apply_E(c, Linv[c], sd[c], rsum, ez)
-                t = eng.vec_op(6, n, eng.zeros(npad), x=b[c], y=cv[c])
-                eng.vec_op(1, n, a[c], a=1.0, x=t, y=ez)                   # :116
-                eng.gemv(self.K, a[c], f_new[c], m=n, n=n)                 # :117
-            if self.allreduce is not None:
-                self.allreduce(f_new)
-            d = eng.vec_op(6, C * n, eng.zeros(C, n), x=f_new, y=f)
-            err = math.sqrt(eng.dot(d, d, C * n))
+            self.step(yd, f, f_new, pi)
+            err = float(self._err[0].item())             # the one read-back of the iteration
+            for ln in self._lanes:
+                ln["eng"].potrf_check()
+            eng.potrf_check()
             self.errors.append(err)
-            f = f_new
+            f, f_new = f_new, f
             if on_iter is not None:
                 on_iter(it, err)
             if err <= tolerance:
                 break
-        _chk(eng, lib.gpx_softmax_classes(eng.h, C, n, n, eng._p(f), eng._p(pi)), "gpx_softmax_classes")
+        eng._sync_stream()
+        _chk(eng, eng.lib.gpx_softmax_classes(eng.h, C, n, n, eng._p(f), eng._p(pi)), "gpx_softmax_classes")
         self.f, self.pi = f, pi
         return len(self.errors)
-
-    def _factor_padded(self, M):
-        eng = self.eng
-        if self.npad > self.n:  # make the padding block the identity again (it may hold a rank-sum)
-            ones = eng.vec_op(4, self.npad - self.n, eng.empty(self.npad - self.n), a=1.0)
-            eng._sync_stream()
-            p = ctypes.c_void_p(M.data_ptr() + 8 * (self.n * M.stride(0) + self.n))
-            _chk(eng, eng.lib.gpx_copy_strided(eng.h, self.npad - self.n, eng._p(ones), 1, p, M.stride(0) + 1), "gpx_copy_strided")
-        return eng.potrf(M)
-
-    def _apply_E(self, c, Linv, sd, x, out):
-        """out = E_c x = D^1/2 L^-T L^-1 D^1/2 x using the stored L_c^-1 (lower, zero upper)."""
-        eng, n, npad = self.eng, self.n, self.npad
-        t = eng.vec_op(2, n, eng.zeros(npad), x=sd, y=x)
-        u = eng.gemv(Linv, t, eng.zeros(npad), m=n, n=n)
-        v = eng.gemv(Linv, u, eng.zeros(npad), trans=True, m=n, n=n)
-        eng.vec_op(2, n, out, x=sd, y=v)
-        return out
 
     def predict(self, X_train_dev, Xs_dev, y, sigma: float = 1.0, l: float = 1.0):
         """f*_c = k*^T (y_c - pi_c) for every class and test point (GP_multi...:193-197) -> (m, C) host."""
