@@ -147,7 +147,7 @@ extern "C" int gpx_gp_fit(gpx_handle h, int kind, const double* X, int64_t n, in
     GPX_REQUIRE(np_ == gpx_padded_dim(n), 11);
     // K + s I, lower tiles only, identity padding            (tune...:306-307, CO2...:142-143)
     gpx_phase_mark(h, GPX_PH_COV);
-    GPX_TRY(gpx_cov_build(h, kind, X, n, X, n, D, theta_host, ntheta, s, GPX_COV_SAME_X | GPX_COV_LOWER, A, np_, np_, lda,
+    GPX_TRY(gpx_cov_build(h, kind, X, n, X, n, D, theta_host, ntheta, s, GPX_COV_SAME_X | GPX_COV_LOWER | GPX_COV_SKIP_UPPER, A, np_, np_, lda,
                           nullptr, 0));
     gpx_phase_mark(h, GPX_PH_POTRF);
     int info = gpx_potrf(h, A, np_, lda, dinv);

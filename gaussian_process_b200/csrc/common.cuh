@@ -112,12 +112,37 @@ int gpx_lml_grad_block(gpx_ctx* h, int kind, const double* X, int64_t n, int D, 
                        const double* Kinv, int64_t ldk, const double* alpha, double* grad, int64_t rows, int64_t cols, int rg0,
                        int cg0);
 int gpx_cov_build_block(gpx_ctx* h, int kind, const double* X, int64_t n, int D, const double* theta_host, int ntheta,
-                        double diag_add, int flags, double* K, int64_t rows, int64_t cols, int64_t ldk, int rg0, int cg0);
+                        double diag_add, int flags, double* K, int64_t rows, int64_t cols, int64_t ldk, int rg0, int cg0,
+                        const double* scale = nullptr);
 int gpx_potrf_block(gpx_ctx* h, double* A, int64_t n, int64_t lda, double* dinv, int goff);
 int gpx_trsm_right_lt_block(gpx_ctx* h, double* B, int64_t m, int64_t ldb, const double* L, int64_t n, int64_t ldl,
                             const double* dinv);
 int gpx_trsm_left_prefix_block(gpx_ctx* h, const double* L, int64_t n, int64_t ldl, const double* dinv, double* B, int64_t ldb,
                                int P, int p, int nb);
+int gpx_trsm_left_prefix_trans_block(gpx_ctx* h, const double* L, int64_t n, int64_t ldl, const double* dinv, double* B,
+                                     int64_t ldb, int P, int p, int nb);
 int gpx_scratch(gpx_ctx* h, size_t bytes, void** out);
 int gpx_scratch2(gpx_ctx* h, size_t bytes, void** out);
 int gpx_read_info(gpx_ctx* h, int* info_host);
+
+// ---- RAII set of timing-less events (multi-stream drivers): destroyed on every exit path (destroying a pending event only
+// defers its release)
+#ifdef __cplusplus
+#include <vector>
+struct GpxEventSet {
+    std::vector<cudaEvent_t> ev;
+    int create(size_t count) {
+        ev.assign(count, nullptr);
+        for (auto& e : ev)
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+                gpx_set_error("gpx: cudaEventCreate failed");
+                return GPX_E_CUDA;
+            }
+        return 0;
+    }
+    ~GpxEventSet() {
+        for (auto e : ev)
+            if (e) cudaEventDestroy(e);
+    }
+};
+#endif

@@ -68,7 +68,10 @@ template <int KIND, bool WITH_DK>
 __global__ void __launch_bounds__(CTHREADS) cov_build_kernel(CovParams p, const double* __restrict__ X1, int64_t n1,
                                                             const double* __restrict__ X2, int64_t n2, double diag_add,
                                                             int flags, double* __restrict__ K, int64_t ldk,
-                                                            double* __restrict__ dK, int64_t dk_stride, int rg0, int cg0) {
+                                                            double* __restrict__ dK, int64_t dk_stride, int rg0, int cg0,
+                                                            const double* __restrict__ scale) {
+    // scale (optional, square blocks): K[i,j] <- scale[i] k_ij scale[j] before the diagonal term is added, so that
+    // B = I + W^1/2 K W^1/2 (GP_binary_classification.py:107) is built straight from X with diag_add = 1.
     // rg0 / cg0: global row / column index of this launch's element (0,0) -- K points at that element; used by
     // the multi-GPU driver to build only the block columns a rank owns.
     __shared__ double xs1[TM * DCH];
@@ -79,7 +82,8 @@ __global__ void __launch_bounds__(CTHREADS) cov_build_kernel(CovParams p, const 
     const bool same = flags & GPX_COV_SAME_X;
     K -= (int64_t)rg0 * ldk + cg0;  // index with global (row, col) below
     if (WITH_DK) dK -= (int64_t)rg0 * ldk + cg0;
-    if ((flags & GPX_COV_LOWER) && col0 > row0) {  // strictly-upper tile: zeros
+    if ((flags & GPX_COV_LOWER) && col0 > row0) {  // strictly-upper tile: zeros (or left untouched)
+        if (flags & GPX_COV_SKIP_UPPER) return;
 #pragma unroll
         for (int i = 0; i < RI; ++i)
 #pragma unroll
@@ -108,6 +112,7 @@ __global__ void __launch_bounds__(CTHREADS) cov_build_kernel(CovParams p, const 
                 const bool diag = (flags & (GPX_COV_SAME_X | GPX_COV_DELTA)) && (r == c);
                 double a = acc[i][j];
                 v = cov_eval<KIND, WITH_DK>(p, a, aux[i][j], diag, dk);
+                if (scale) v = scale[r] * v * scale[c];
                 if (diag) v += diag_add;
             } else {
                 v = (same && r == c) ? 1.0 : 0.0;
@@ -222,20 +227,20 @@ int make_params(int kind, int D, const double* theta, int ntheta, CovParams* p) 
 template <bool WITH_DK>
 int launch_build(gpx_ctx* h, const CovParams& p, const double* X1, int64_t n1, const double* X2, int64_t n2, double diag_add,
                  int flags, double* K, int64_t n1p, int64_t n2p, int64_t ldk, double* dK, int64_t dk_stride, int rg0 = 0,
-                 int cg0 = 0) {
+                 int cg0 = 0, const double* scale = nullptr) {
     dim3 grid((unsigned)(n2p / TN), (unsigned)(n1p / TM));
     switch (p.kind) {
         case GPX_COV_SE:
-            cov_build_kernel<GPX_COV_SE, WITH_DK><<<grid, CTHREADS, 0, h->stream>>>(p, X1, n1, X2, n2, diag_add, flags, K, ldk, dK, dk_stride, rg0, cg0);
+            cov_build_kernel<GPX_COV_SE, WITH_DK><<<grid, CTHREADS, 0, h->stream>>>(p, X1, n1, X2, n2, diag_add, flags, K, ldk, dK, dk_stride, rg0, cg0, scale);
             break;
         case GPX_COV_LIN:
-            cov_build_kernel<GPX_COV_LIN, WITH_DK><<<grid, CTHREADS, 0, h->stream>>>(p, X1, n1, X2, n2, diag_add, flags, K, ldk, dK, dk_stride, rg0, cg0);
+            cov_build_kernel<GPX_COV_LIN, WITH_DK><<<grid, CTHREADS, 0, h->stream>>>(p, X1, n1, X2, n2, diag_add, flags, K, ldk, dK, dk_stride, rg0, cg0, scale);
             break;
         case GPX_COV_PER:
-            cov_build_kernel<GPX_COV_PER, WITH_DK><<<grid, CTHREADS, 0, h->stream>>>(p, X1, n1, X2, n2, diag_add, flags, K, ldk, dK, dk_stride, rg0, cg0);
+            cov_build_kernel<GPX_COV_PER, WITH_DK><<<grid, CTHREADS, 0, h->stream>>>(p, X1, n1, X2, n2, diag_add, flags, K, ldk, dK, dk_stride, rg0, cg0, scale);
             break;
         default:
-            cov_build_kernel<GPX_COV_CO2, WITH_DK><<<grid, CTHREADS, 0, h->stream>>>(p, X1, n1, X2, n2, diag_add, flags, K, ldk, dK, dk_stride, rg0, cg0);
+            cov_build_kernel<GPX_COV_CO2, WITH_DK><<<grid, CTHREADS, 0, h->stream>>>(p, X1, n1, X2, n2, diag_add, flags, K, ldk, dK, dk_stride, rg0, cg0, scale);
             break;
     }
     GPX_CHECK_LAUNCH(h);
@@ -334,10 +339,11 @@ int gpx_lml_grad_block(gpx_ctx* h, int kind, const double* X, int64_t n, int D, 
 
 // Covariance block whose element (0,0) has global index (rg0, cg0): rows x cols elements written at K (ld ldk).
 int gpx_cov_build_block(gpx_ctx* h, int kind, const double* X, int64_t n, int D, const double* theta_host, int ntheta,
-                        double diag_add, int flags, double* K, int64_t rows, int64_t cols, int64_t ldk, int rg0, int cg0) {
+                        double diag_add, int flags, double* K, int64_t rows, int64_t cols, int64_t ldk, int rg0, int cg0,
+                        const double* scale) {
     CovParams p;
     GPX_TRY(make_params(kind, D, theta_host, ntheta, &p));
-    return launch_build<false>(h, p, X, n, X, n, diag_add, flags, K, rows, cols, ldk, nullptr, 0, rg0, cg0);
+    return launch_build<false>(h, p, X, n, X, n, diag_add, flags, K, rows, cols, ldk, nullptr, 0, rg0, cg0, scale);
 }
 
 extern "C" int gpx_lml_grad(gpx_handle h, int kind, const double* X, int64_t n, int D, const double* theta_host, int ntheta,

@@ -419,24 +419,6 @@ __global__ void copy_tiles_kernel(double* __restrict__ dst, int64_t ldd, int64_t
 
 
 namespace {
-// Events of one factorisation; destroyed on every exit path (destroying a pending event only defers its release).
-struct EventSet {
-    std::vector<cudaEvent_t> ev;
-    int create(size_t count) {
-        ev.assign(count, nullptr);
-        for (auto& e : ev)
-            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
-                gpx_set_error("potrf: cudaEventCreate failed");
-                return GPX_E_CUDA;
-            }
-        return 0;
-    }
-    ~EventSet() {
-        for (auto e : ev)
-            if (e) cudaEventDestroy(e);
-    }
-};
-
 // Right-looking blocked Cholesky with LOOK-AHEAD on two streams (used below a size threshold where the serial chain of
 // small kernels, not the DMMA pipe, bounds the recursive formulation).  Panel width nb; after panel j is final:
 //   chain stream H (high priority): a. update block column j+1 with panel j   b. factor panel j+1 (diag potrf + TRSM)
@@ -450,7 +432,7 @@ int potrf_la(gpx_ctx* h, double* A, int64_t n, int64_t lda, double* dinv, int go
     const int64_t nblk = n / nb;
     const int tpb = nb / LT;
     cudaStream_t S = h->stream, H = h->aux_stream;
-    EventSet es;
+    GpxEventSet es;
     GPX_TRY(es.create(2 * nblk + 1));
     cudaEvent_t* evP = es.ev.data();
     cudaEvent_t* evS = evP + nblk;
@@ -527,7 +509,7 @@ int potrf_la_split(gpx_ctx* h, double* A, int64_t n, int64_t lda, double* dinv, 
     const int tpb = nb / LT;
     cudaStream_t S = h->stream, H = h->aux_stream, H2 = h->aux2_stream;
     enum { LEAF = 0, TOP, PAN, U1, U2, SD, NEV };
-    EventSet es;
+    GpxEventSet es;
     GPX_TRY(es.create(NEV * nblk + 2));
     auto E = [&](int kind, int64_t j) -> cudaEvent_t { return es.ev[kind * nblk + j]; };
     int rc = 0;
@@ -829,6 +811,48 @@ int gpx_trsm_left_prefix_block(gpx_ctx* h, const double* L, int64_t n, int64_t l
                                int P, int p, int nb) {
     PrefixMap pm{P, p, nb};
     return trsm_left_prefix(h, L, n, ldl, dinv, B, ldb, 0, pm);
+}
+
+namespace {
+// Backward counterpart:  L^T Z = X  restricted to the entries on/below each column block's own diagonal block (row >= start
+// of the column's global block) -- all a symmetric result needs.  Back substitution produces the bottom rows first and
+// rows >= r of Z depend only on rows >= r of X, so the restriction is exact; rows of this sub-problem use the local
+// columns whose global block starts below the end of the row range (the same prefix structure), and output tiles that
+// lie entirely above a column's block start are skipped (lower_only with the block-cyclic column map).  N^3/(3P) flops.
+int trsm_left_prefix_trans(gpx_ctx* h, const double* L, int64_t n, int64_t ldl, const double* dinv, double* B, int64_t ldb,
+                           int64_t grow0, const PrefixMap& pm) {
+    const int64_t ncols = prefix_cols(pm, grow0 + n);
+    if (ncols <= 0) return 0;
+    if (n == LT) {
+        GemmArgs a = base_args();  // Z = Dinv^T X (in place; a CTA reads exactly the column range it writes)
+        a.A = dinv; a.lda = LT; a.a_kmajor = 0;
+        a.B = B; a.ldb = ldb; a.b_kmajor = 0;
+        a.C = B; a.ldc = ldb;
+        a.M = LT; a.N = (int)ncols; a.K = LT;
+        return gpx_gemm_launch(h, a);
+    }
+    const int64_t h1 = half_tiles(n), h2 = n - h1;
+    GPX_TRY(trsm_left_prefix_trans(h, L + h1 * ldl + h1, h2, ldl, dinv + (h1 / LT) * LT * LT, B + h1 * ldb, ldb, grow0 + h1, pm));
+    const int64_t nc1 = prefix_cols(pm, grow0 + h1);   // columns that have rows in the top half
+    if (nc1 > 0) {
+        GemmArgs a = base_args();  // X1[:, :nc1] -= L21^T Z2[:, :nc1]
+        a.A = L + h1 * ldl; a.lda = ldl; a.a_kmajor = 0;
+        a.B = B + h1 * ldb; a.ldb = ldb; a.b_kmajor = 0;
+        a.C = B; a.ldc = ldb;
+        a.M = (int)h1; a.N = (int)nc1; a.K = (int)h2;
+        a.alpha = -1.0; a.beta = 1.0;
+        a.lower_only = 1;   // rows above a column's block start are never needed
+        a.cyc_P = pm.P; a.cyc_p = pm.p; a.cyc_tpb = pm.nb / LT; a.cyc_q0 = 0; a.cyc_row_base = (int)grow0; a.cyc_b_rows = 0;
+        GPX_TRY(gpx_gemm_launch(h, a));
+    }
+    return trsm_left_prefix_trans(h, L, h1, ldl, dinv, B, ldb, grow0, pm);
+}
+}  // namespace
+
+int gpx_trsm_left_prefix_trans_block(gpx_ctx* h, const double* L, int64_t n, int64_t ldl, const double* dinv, double* B,
+                                     int64_t ldb, int P, int p, int nb) {
+    PrefixMap pm{P, p, nb};
+    return trsm_left_prefix_trans(h, L, n, ldl, dinv, B, ldb, 0, pm);
 }
 
 extern "C" int gpx_debug_leaf_cycles(long long* out4) {

@@ -115,12 +115,13 @@ class Engine:
 
     # ------------------------------------------------------------------ A1-A3 covariance
     def cov(self, kind: int, X1, X2, theta, diag_add: float = 0.0, same_x: bool = False, lower: bool = False,
-            out=None, with_grad: bool = False, delta: bool = False):
-        """K (padded) = k(X1, X2; theta) [+ diag_add I].  Returns K or (K, dK[ntheta]) device tensors."""
+            out=None, with_grad: bool = False, delta: bool = False, n1p: Optional[int] = None):
+        """K (padded) = k(X1, X2; theta) [+ diag_add I].  Returns K or (K, dK[ntheta]) device tensors.
+        ``n1p`` overrides the padded row count (a factor padded to the multi-GPU block unit has more rows)."""
         self._sync_stream()
         n1, D = X1.shape
         n2 = X2.shape[0]
-        n1p, n2p = padded(n1), padded(n2)
+        n1p, n2p = (padded(n1) if n1p is None else int(n1p)), padded(n2)
         K = out if out is not None else self.empty(n1p, n2p)
         th, thp = _theta_array(theta)
         flags = (COV_SAME_X if same_x else 0) | (COV_LOWER if lower else 0) | (COV_DELTA if delta else 0)
@@ -398,18 +399,30 @@ class Engine:
                     converged=bool(out[5]))
 
     # ------------------------------------------------------------------ A6 prediction
-    def predict(self, fit: GPFit, Xs, want_v: bool = False, kss_diag=None):
+    def predict(self, fit: GPFit, Xs, want_v: bool = False, kss_diag=None, m_total: Optional[int] = None, row0: int = 0):
         """mu = K_s^T alpha, var = diag(K_ss) - colsum((L^-1 K_s)^2)  (GP_regression.py:143-147).
 
-        Returns (mu, var, V or None) as device tensors of the true test size (V is padded)."""
+        Returns (mu, var, V or None) as device tensors of the true test size (V is padded).  When ``Xs`` is one shard of
+        a larger test set, ``m_total`` is the size of the whole set and ``row0`` the shard's first index in it: the CO2
+        kernel's "square block" delta (CO2_example.py:58-66) is decided from the WHOLE block's shape and lands on the
+        global diagonal."""
         self._sync_stream()
         if fit.L_is_inverse:
             raise GpxError("predict() needs the factor L; this fit holds L^-1 (fit_grad overwrote it)")
         Xsd = self.to_device(Xs)
         m = Xsd.shape[0]
         # CO2_example.py:58-66 adds theta_11^2 * I to ANY square block, so also to K_s when N == n
-        square_co2 = fit.kind == COV_CO2 and fit.n == m
-        Ks = self.cov(fit.kind, fit.X, Xsd, fit.theta, delta=square_co2)    # (npad, mpad)
+        square_co2 = fit.kind == COV_CO2 and fit.n == (m if m_total is None else int(m_total))
+        if square_co2 and m_total is not None and (m != m_total or row0 != 0):
+            # a shard of a square cross block: build without the delta, then add theta_11^2 on the global diagonal
+            Ks = self.cov(fit.kind, fit.X, Xsd, fit.theta, n1p=fit.npad)
+            cnt = max(0, min(m, fit.n - row0))
+            if cnt > 0:
+                d = self.vec_op(4, cnt, self.empty(cnt), a=float(fit.theta[10]) ** 2)
+                view = Ks[row0:row0 + cnt, :cnt]
+                view.diagonal().add_(d)      # torch as buffer arithmetic on cnt entries (host-side logic of a rare corner case)
+        else:
+            Ks = self.cov(fit.kind, fit.X, Xsd, fit.theta, delta=square_co2, n1p=fit.npad)    # (npad, mpad)
         mu = self.empty(m)
         var = self.empty(m)
         lib = self.lib
@@ -491,6 +504,64 @@ class Engine:
         check(st, "gpx_mg_fit_grad")
         o = self.to_host(out)
         return float(o[0]), (o[3:3 + len(th)].copy() if with_grad else None), alpha
+
+    def mg_layout(self, n: int, nb: int):
+        """dict(Aloc, Kloc, Lfull, dinv (element offsets into the workspace), npad, wloc)."""
+        world = getattr(self, "_mg_world", 1)
+        out = (ctypes.c_int64 * 6)()
+        check(self.lib.gpx_mg_workspace_layout(n, nb, world, out), "gpx_mg_workspace_layout")
+        return dict(Aloc=out[0], Kloc=out[1], Lfull=out[2], dinv=out[3], npad=out[4], wloc=out[5])
+
+    def mg_workspace(self, n: int, nb: int):
+        world = getattr(self, "_mg_world", 1)
+        return self.empty(int(self.lib.gpx_mg_workspace_elems(n, nb, world)))
+
+    def mg_fit(self, kind: int, X, y, theta, s: float, nb: int = 256, ws=None) -> GPFit:
+        """Distributed fit (no gradient) -> a GPFit whose factor is the REPLICATED factor inside the workspace: every
+        rank can predict its own shard of test points from it without refitting (``mg_predict``)."""
+        self._sync_stream()
+        Xd = self.to_device(X)
+        yd = self.to_device(np.asarray(y).reshape(-1) if not hasattr(y, "data_ptr") else y.reshape(-1))
+        n, D = Xd.shape
+        th, thp = _theta_array(theta)
+        ws = self.mg_workspace(n, nb) if ws is None else ws
+        lay = self.mg_layout(n, nb)
+        npad = lay["npad"]
+        alpha = self.empty(npad)
+        out = self.empty(3 + 11)
+        check(self.lib.gpx_mg_fit_grad(self.h, kind, self._p(Xd), n, D, thp, len(th), float(s), self._p(yd), nb, self._p(ws),
+                                       self._p(alpha), self._p(out), ctypes.c_void_p(out.data_ptr() + 24), 0), "gpx_mg_fit_grad")
+        o = self.to_host(out)
+        L = ws[lay["Lfull"]:lay["Lfull"] + npad * npad].view(npad, npad)
+        dinv = ws[lay["dinv"]:lay["dinv"] + npad * GPX_TILE].view(npad // GPX_TILE, GPX_TILE, GPX_TILE)
+        fit = GPFit(kind, th, float(s), n, npad, Xd, yd, L, dinv, alpha, float(o[0]), float(o[1]), float(o[2]))
+        fit.ws = ws          # keeps the workspace alive
+        return fit
+
+    def mg_predict(self, fit: GPFit, Xs):
+        """Test-point prediction split over the ranks: every rank predicts a contiguous shard of ``Xs`` from
+        the replicated factor of ``mg_fit`` and the (mu, var) slices are all-gathered.  Host arrays out."""
+        from . import parallel as P
+        import torch.distributed as dist
+        Xs = np.asarray(Xs, dtype=np.float64)
+        m = Xs.shape[0]
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank() if world > 1 else 0
+        lo, hi = P.shard_range(m, rank, world)
+        if hi > lo:
+            mu, var, _ = self.predict(fit, Xs[lo:hi], m_total=m, row0=lo)
+            loc = np.stack([self.to_host(mu), self.to_host(var)], axis=1)
+        else:
+            loc = np.zeros((0, 2))
+        full = P.gather_slices(loc, m) if world > 1 else loc
+        return full[:, 0].copy(), full[:, 1].copy()
+
+    def mg_factor(self, kind: int, Xd, theta, diag_add: float, scale, nb: int, ws):
+        """Distributed Cholesky of diag(scale) k(X,X) diag(scale) + diag_add I into the workspace's replicated factor."""
+        self._sync_stream()
+        th, thp = _theta_array(theta)
+        check(self.lib.gpx_mg_factor(self.h, kind, self._p(Xd), Xd.shape[0], Xd.shape[1], thp, len(th), float(diag_add),
+                                     self._p(scale), nb, self._p(ws)), "gpx_mg_factor")
 
     def mg_emulate_fit_grad(self, P: int, kind: int, X, y, theta, s: float, nb: int = 256):
         """P virtual ranks on this one GPU (test helper for the block-cyclic index maps)."""

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define GPX_VERSION 100
+#define GPX_VERSION 200
 #define GPX_TILE 128
 
 #define GPX_E_CUDA   (-100)   /* a CUDA runtime call failed            */
@@ -52,6 +52,8 @@ enum gpx_cov_kind {
 /* flags for gpx_cov_build */
 #define GPX_COV_SAME_X   1   /* X1 is X2: square block; theta11^2 delta (CO2) and `diag_add` go on the diagonal */
 #define GPX_COV_LOWER    2   /* only tiles on/below the diagonal are computed; strictly-upper tiles are zeroed  */
+#define GPX_COV_SKIP_UPPER 8 /* with GPX_COV_LOWER: strictly-upper tiles are not written at all (the caller's factorisation
+                                never reads them and gpx_potrf zeroes them at the end): saves half of the HBM writes       */
 #define GPX_COV_DELTA    4   /* n1 == n2 but X1 is not X2 (a square CROSS block): the CO2 delta term still goes on
                                 the diagonal (CO2_example.py:58-66 tests the shape only); padding stays zero        */
 
@@ -231,24 +233,44 @@ int gpx_debug_leaf_cycles(long long* out4);
 
 /* ---- multi-GPU (one process per GPU; NCCL communicator owned by the handle) -----------------
  * Layout: 1-D block-cyclic block columns of width nb (a P x 1 grid of the 2-D block-cyclic scheme), panels
- * broadcast with NCCL and kept in a replicated factor; see nccl_mg.cu.  NCCL is dlopen'ed at run time. */
+ * broadcast with NCCL and kept in a replicated factor, trailing updates grouped to K = 1024; K^-1 by two local
+ * prefix-structured TRSMs (no all-gather); see nccl_mg.cu.  NCCL is dlopen'ed at run time. */
 int     gpx_nccl_load(const char* libnccl_path);                        /* optional explicit path */
 int     gpx_nccl_unique_id(void* id128);                                /* rank 0: fills 128 bytes */
 int     gpx_nccl_init(gpx_handle h, const void* id128, int rank, int world);
+int     gpx_mg_set_group_k(int k);                                      /* K of the grouped trailing update (default 1024) */
 int64_t gpx_mg_padded_dim(int64_t n, int nb, int world);                /* n rounded up to nb*world */
 int64_t gpx_mg_workspace_elems(int64_t n, int nb, int world);           /* doubles of device workspace per rank */
+/* Element offsets of the pieces inside the workspace: out6 = {Aloc, Kloc (local block columns of K^-1 after a fit with
+ * gradient; rows on/below each block's diagonal block are valid), Lfull (replicated factor: npad x npad row-major, clean lower
+ * triangle), dinv (its leaf inverses), npad, wloc}. */
+int gpx_mg_workspace_layout(int64_t n, int nb, int world, int64_t* out6);
 /* This rank's part of the distributed fit + LML (+ gradient when with_grad): tune...:123-145 on P GPUs.
  * X (n x D), y (n), alpha (npad), out3 (3), grad (ntheta) are device pointers; every rank gets the same
- * alpha / out3 / grad.  Returns >0 (first bad pivot) on every rank if the matrix is not positive definite. */
+ * alpha / out3 / grad.  Returns >0 (first bad pivot) on every rank if the matrix is not positive definite.  After the
+ * call the workspace holds the replicated factor (with_grad = 0 or 1) and, with_grad = 1, this rank's block columns of K^-1. */
 int gpx_mg_fit_grad(gpx_handle h, int kind, const double* X, int64_t n, int D, const double* theta_host, int ntheta,
                     double s, const double* y, int nb, double* ws, double* alpha, double* out3, double* grad, int with_grad);
+/* The distributed (block-cyclic, NCCL panel broadcast) Cholesky on its own: factors
+ *   M = diag(scale) k(X, X; theta) diag(scale) + diag_add I      (scale may be NULL)
+ * and leaves the replicated factor in the workspace.  scale = W^1/2, diag_add = 1 is the Laplace matrix
+ * B = I + W^1/2 K W^1/2 of GP_binary_classification.py:107. */
+int gpx_mg_factor(gpx_handle h, int kind, const double* X, int64_t n, int D, const double* theta_host, int ntheta,
+                  double diag_add, const double* scale, int nb, double* ws);
+/* x <- (L L^T)^-1 x with the replicated factor in the workspace (x: npad doubles, zero padded); no communication. */
+int gpx_mg_potrs_vec(gpx_handle h, int64_t n, int nb, double* ws, double* x);
+/* One textbook Newton iteration of the binary Laplace approximation (GP_binary_classification.py:104-111) with B factored
+ * by the distributed Cholesky: K (np x np, ld) is the replicated covariance used for the two O(N^2) mat-vecs, X / theta its
+ * inputs (B is built block-cyclically from them).  y, f, f_new: npad doubles; vws: 8 npad doubles (vws[0..npad) = gradient,
+ * [npad..2 npad) = W, [2 npad..3 npad) = W^1/2 on return); err_dev[0] = |f_new - f|_2. */
+int gpx_mg_laplace_binary_step(gpx_handle h, int kind, const double* X, int64_t n, int D, const double* theta_host,
+                               int ntheta, const double* K, int64_t ld, const double* y, const double* f, int nb,
+                               double* ws, double* vws, double* f_new, double* err_dev);
 /* Test helper: the same per-rank routines driven for P virtual ranks on ONE GPU (collectives become copies);
  * ws_all = P * gpx_mg_workspace_elems(n, nb, P) doubles. */
 int gpx_mg_emulate_fit_grad(gpx_handle h, int P, int kind, const double* X, int64_t n, int D, const double* theta_host,
                             int ntheta, double s, const double* y, int nb, double* ws_all, double* alpha, double* out3,
                             double* grad);
-/* The distributed (block-cyclic) Cholesky of SURVEY 8e is the factorisation phase of gpx_mg_fit_grad: with_grad = 0 stops
- * after factor + alpha + LML, so there is no separate gpx_potrf_mg entry point. */
 
 /* ---- host-buffer drop-in calls (HOST pointers; copies inside; synchronous) ------------------*/
 /* LML (+ optional gradient wrt all theta when grad_host != NULL) of y ~ GP(0, cov + s I). */

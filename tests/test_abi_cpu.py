@@ -28,7 +28,7 @@ def test_version_and_padding_without_gpu():
     if not os.path.isfile(_lib.LIB_PATH):
         pytest.skip("libgpx.so not built")
     lib = _lib.load()
-    assert lib.gpx_version() == 100
+    assert lib.gpx_version() == 200
     assert lib.gpx_padded_dim(1) == 128 and lib.gpx_padded_dim(128) == 128 and lib.gpx_padded_dim(129) == 256
     assert lib.gpx_small_max() == 128
 

@@ -35,15 +35,24 @@ def main():
         print("world=%d lml rel %.2e grad rel %.2e alpha rel %.2e" % (dist.get_world_size(), e1, e2, e3))
         assert e1 < 1e-8 and e2 < 1e-7 and e3 < 1e-7
         print("MG_CHECK_OK")
-    # ---- sharded prediction (test points split over ranks) and class-sharded multiclass Laplace
-    from gaussian_process_b200.distributed import multiclass_newton_sharded, predict_sharded
-    from gaussian_process_b200.engine import padded
+    # ---- sharded prediction (test points split over ranks) from the REPLICATED factor of the distributed fit
+    from gaussian_process_b200.distributed import BinaryLaplaceDistributed, multiclass_newton_sharded, predict_sharded
     Xc, yc, Xs = O.synth_c1(200, 333)
-    fit = eng.fit(COV_SE, Xc, yc, [1.0, 1.0], 5e-4)
-    mu, var = predict_sharded(eng, fit, Xs)
     np.random.seed(0)
     mu_o, sd_o, _ = O.regression_prediction(Xc, Xs, yc, 'rbf', 1, 1)
-    assert np.max(np.abs(mu - mu_o)) < 1e-8 * np.max(np.abs(mu_o)) and np.max(np.abs(var - sd_o ** 2)) < 1e-8 * np.max(sd_o ** 2)
+    fit = eng.mg_fit(COV_SE, Xc, yc, [1.0, 1.0], 5e-4, nb=128)
+    for mu, var in (eng.mg_predict(fit, Xs), predict_sharded(eng, eng.fit(COV_SE, Xc, yc, [1.0, 1.0], 5e-4), Xs)):
+        assert np.max(np.abs(mu - mu_o)) < 1e-8 * np.max(np.abs(mu_o)) and np.max(np.abs(var - sd_o ** 2)) < 1e-8 * np.max(sd_o ** 2)
+    # ---- binary Laplace with B factored by the distributed Cholesky
+    Xb, yb, _ = O.synth_c3(1500, 8)
+    mb = BinaryLaplaceDistributed(eng, Xb, 1.0, 1.0, nb=128)
+    itb = mb.fit_newton(yb, tolerance=1e-9)
+    f_ob = O.binary_training_newton(O.rbf_kernel(Xb, Xb, 1, 1), yb, tolerance=1e-9)
+    eb = float(np.max(np.abs(eng.to_host(mb.f[:1500]) - f_ob[0])) / np.max(np.abs(f_ob[0])))
+    assert itb == f_ob[4] and eb < 1e-6, (itb, f_ob[4], eb)
+    if dist.get_rank() == 0:
+        print("distributed binary Laplace rel err %.2e after %d Newton steps" % (eb, itb))
+        print("MG_LAPLACE_OK")
     Xm, labels, ym, Xt, tl = O.synth_c4(n=300, C=5, D=6, n_test=10)
     Xd = eng.to_device(Xm)
     Kd = eng.cov(COV_SE, Xd, Xd, [1.0, 1.0], same_x=True)
