@@ -67,6 +67,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--block", dest="nb", type=int, default=256, help="block-cyclic block width of the multi-GPU path")
     ap.add_argument("--mg", action="store_true", help="use the block-cyclic multi-GPU driver even at world size 1")
+    ap.add_argument("--dump-launches", default="", help="write a per-GEMM-launch CSV (phase, shape, ms) of the timed region")
     ap.add_argument("--parity-n", type=int, default=4096, help="size of the in-run multi-GPU parity check (0 = off)")
     return ap.parse_args()
 
@@ -618,6 +619,8 @@ def run_gpx(args, n, D):
     for e in w.timing_handles:
         tbuf = (ctypes.c_double * 16)()
         check(lib.gpx_timing_collect(e.h, tbuf, 16), "gpx_timing_collect")
+        if args.dump_launches and e is eng:
+            check(lib.gpx_timing_dump(e.h, (args.dump_launches + ".rank%d.csv" % rank).encode()), "gpx_timing_dump")
         check(lib.gpx_timing_enable(e.h, 0), "gpx_timing_enable")
         gemm_ms += tbuf[0] / steps
         gemm_launches += tbuf[1] / steps

@@ -31,7 +31,7 @@ struct gpx_ctx {
 // phases of the fused drivers (gpx_timing_collect out[3 + phase])
 enum { GPX_PH_COV = 0, GPX_PH_POTRF = 1, GPX_PH_SOLVE = 2, GPX_PH_TRTRI = 3, GPX_PH_LAUUM = 4, GPX_PH_GRAD = 5,
        GPX_PH_END = 6, GPX_NPHASES = 8 };
-void gpx_timing_gemm_begin(gpx_ctx* h, double flops_exec);
+void gpx_timing_gemm_begin(gpx_ctx* h, double flops_exec, int M = 0, int N = 0, int K = 0);
 void gpx_timing_gemm_end(gpx_ctx* h);
 void gpx_timing_leaf_begin(gpx_ctx* h);
 void gpx_timing_leaf_end(gpx_ctx* h);

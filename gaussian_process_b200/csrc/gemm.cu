@@ -214,7 +214,7 @@ int launch_t(gpx_ctx* h, const GemmArgs& a) {
         configured = true;
     }
     dim3 grid(a.N / TN, a.M / BM, (a.batch > 0 ? a.batch : 1) * (a.batch2 > 1 ? a.batch2 : 1));
-    if (h->timing_on) gpx_timing_gemm_begin(h, exec_flops(a, TN));
+    if (h->timing_on) gpx_timing_gemm_begin(h, exec_flops(a, TN), a.M, a.N, a.K);
     dgemm_dmma_kernel<A_KM, B_KM, TN><<<grid, C_::NT, C_::SMEM, h->stream>>>(a);
     GPX_CHECK_LAUNCH(h);
     gpx_timing_gemm_end(h);

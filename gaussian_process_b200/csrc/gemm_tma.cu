@@ -280,7 +280,7 @@ int gpx_gemm_tma_try_launch(gpx_ctx* h, const GemmArgs& a, double flops_exec) {
     if ((a.a_kmajor ? make_map(&mapA, a.A, a.M, a.K, a.lda, BM) : make_map_ks(&mapA, a.A, a.M, a.K, a.lda)) != 0) return 0;
     if ((a.b_kmajor ? make_map(&mapB, a.B, rowsB, a.K, a.ldb, TN) : make_map_ks(&mapB, a.B, rowsB, a.K, a.ldb)) != 0) return 0;
     dim3 grid(a.N / TN, a.M / BM, 1);
-    if (h->timing_on) gpx_timing_gemm_begin(h, flops_exec);
+    if (h->timing_on) gpx_timing_gemm_begin(h, flops_exec, a.M, a.N, a.K);
     if (a.a_kmajor && a.b_kmajor) dgemm_dmma_tma_kernel<true, true, TN><<<grid, TCfg<TN>::NT, TCfg<TN>::SMEM, h->stream>>>(mapA, mapB, a);
     else if (a.a_kmajor) dgemm_dmma_tma_kernel<true, false, TN><<<grid, TCfg<TN>::NT, TCfg<TN>::SMEM, h->stream>>>(mapA, mapB, a);
     else if (a.b_kmajor) dgemm_dmma_tma_kernel<false, true, TN><<<grid, TCfg<TN>::NT, TCfg<TN>::SMEM, h->stream>>>(mapA, mapB, a);

@@ -340,8 +340,11 @@ int factor_rank(MgRank& r, const MgBuild& b, int* info_out) {
             const size_t count = (size_t)rows * r.nb + (size_t)r.tpb * GPX_T * GPX_T;
             const int64_t g = j / r.G, j0 = g * r.G;
             const int gw = (int)std::min<int64_t>(r.G, r.nblk - j0);
-            // ---- communication stream: broadcast panel j as soon as its owner has packed it, unpack into the factor
-            if (owner == r.p) GPX_CUDA(cudaStreamWaitEvent(Cs, evPanel[sb], 0));
+            // ---- communication stream: broadcast panel j as soon as its owner has packed it, unpack into the factor.
+            // Non-owners gate their side of the broadcast on the point of their OWN compute stream at which the owner
+            // (running in lock-step) is about to finish the panel: a receive kernel launched earlier would spin on
+            // ~20 SMs' worth of registers for a whole step and slow the bulk GEMM by ~14 % (measured at 2 GPUs).
+            GPX_CUDA(cudaStreamWaitEvent(Cs, evPanel[sb], 0));
             if (P > 1) GPX_NCCL(g_nccl.Broadcast(r.stage[sb], r.stage[sb], count, NCCL_F64, owner, (ncclComm_p)h->nccl_comm, Cs));
             GPX_TRY(panel_unpack(r, j, r.stage[sb], Cs));
             GPX_CUDA(cudaEventRecord(evRecv[sb], Cs));
@@ -349,6 +352,7 @@ int factor_rank(MgRank& r, const MgBuild& b, int* info_out) {
             if (have_prev) GPX_TRY(bulk_chunk(r, prev, (int)(j - j0)));
             GPX_CUDA(cudaStreamWaitEvent(S, evRecv[sb], 0));
             GPX_TRY(rank_step(r, j, r.stage[sb ^ 1], on_panel));
+            if (j + 1 < r.nblk && (int)((j + 1) % P) != r.p) GPX_CUDA(cudaEventRecord(evPanel[sb ^ 1], S));   // the gate above
             if (j == j0 + gw - 1) {   // group complete: its bulk update is deferred into the steps of the next group
                 const int64_t jn0 = j0 + gw;
                 const int gw_next = jn0 < r.nblk ? (int)std::min<int64_t>(r.G, r.nblk - jn0) : 0;

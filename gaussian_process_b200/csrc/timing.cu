@@ -10,6 +10,9 @@ struct gpx_timing {
     std::vector<std::pair<size_t, size_t>> leaf_pairs;   // potrf leaf launches
     double gemm_flops_exec = 0.0;       // flops the kernel actually executes (tile-granular k ranges)
     std::vector<std::pair<int, size_t>> marks;            // (phase id, event index)
+    struct Shape { int M, N, K, phase; double flops; };
+    std::vector<Shape> gemm_shapes;                       // one per gemm_pairs entry
+    int cur_phase = -1;
 };
 
 static cudaEvent_t next_event(gpx_timing* t, size_t* idx) {
@@ -22,13 +25,14 @@ static cudaEvent_t next_event(gpx_timing* t, size_t* idx) {
     return t->pool[t->used++];
 }
 
-void gpx_timing_gemm_begin(gpx_ctx* h, double flops_exec) {
+void gpx_timing_gemm_begin(gpx_ctx* h, double flops_exec, int M, int N, int K) {
     if (!h->timing_on) return;
     gpx_timing* t = (gpx_timing*)h->timing;
     size_t i0;
     cudaEvent_t e0 = next_event(t, &i0);
     cudaEventRecord(e0, h->stream);
     t->gemm_pairs.push_back({i0, (size_t)-1});
+    t->gemm_shapes.push_back({M, N, K, t->cur_phase, flops_exec});
     t->gemm_flops_exec += flops_exec;
 }
 
@@ -64,6 +68,7 @@ void gpx_phase_mark(gpx_ctx* h, int phase) {
     cudaEvent_t e = next_event(t, &i);
     cudaEventRecord(e, h->stream);
     t->marks.push_back({phase, i});
+    t->cur_phase = phase;
 }
 
 extern "C" int gpx_timing_enable(gpx_handle h, int on) {
@@ -72,6 +77,8 @@ extern "C" int gpx_timing_enable(gpx_handle h, int on) {
     gpx_timing* t = (gpx_timing*)h->timing;
     t->used = 0;
     t->gemm_pairs.clear();
+    t->gemm_shapes.clear();
+    t->cur_phase = -1;
     t->leaf_pairs.clear();
     t->marks.clear();
     t->gemm_flops_exec = 0.0;
@@ -111,6 +118,27 @@ extern "C" int gpx_timing_collect(gpx_handle h, double* out, int nout) {
         int p = t->marks[m].first;
         if (p >= 0 && p < GPX_NPHASES) out[3 + p] += ms;
     }
+    return 0;
+}
+
+// Per-launch CSV of the instrumented region (call after gpx_timing_collect, before the next gpx_timing_enable):
+// index, phase, M, N, K, flops executed, ms, start offset (ms after the first recorded event).
+extern "C" int gpx_timing_dump(gpx_handle h, const char* path) {
+    GPX_REQUIRE(h != nullptr && h->timing != nullptr && path != nullptr, 1);
+    gpx_timing* t = (gpx_timing*)h->timing;
+    FILE* f = fopen(path, "w");
+    GPX_REQUIRE(f != nullptr, 2);
+    fprintf(f, "idx,phase,M,N,K,flops,ms,start_ms\n");
+    for (size_t i = 0; i < t->gemm_pairs.size(); ++i) {
+        auto& pr = t->gemm_pairs[i];
+        if (pr.second == (size_t)-1) continue;
+        float ms = 0.f, st = 0.f;
+        cudaEventElapsedTime(&ms, t->pool[pr.first], t->pool[pr.second]);
+        cudaEventElapsedTime(&st, t->pool[0], t->pool[pr.first]);
+        const auto& sh = t->gemm_shapes[i];
+        fprintf(f, "%zu,%d,%d,%d,%d,%.0f,%.4f,%.4f\n", i, sh.phase, sh.M, sh.N, sh.K, sh.flops, ms, st);
+    }
+    fclose(f);
     return 0;
 }
 

@@ -227,6 +227,8 @@ int gpx_bench_fp64_peak(gpx_handle h, int use_dmma, int iters, double* tflops_ou
  * phase p (0 cov build, 1 potrf, 2 solves+LML, 3 trtri, 4 lauum, 5 gradient).  nout >= 11. */
 int gpx_timing_enable(gpx_handle h, int on);
 int gpx_timing_collect(gpx_handle h, double* out, int nout);
+/* per-launch CSV (phase, M, N, K, flops executed, ms, start offset) of the instrumented region; after gpx_timing_collect */
+int gpx_timing_dump(gpx_handle h, const char* path);
 
 /* debug hook: cycles spent by the last potrf leaf kernel in {load, factor, inverse, store} (clock64) */
 int gpx_debug_leaf_cycles(long long* out4);
