@@ -103,8 +103,32 @@ struct GemmArgs {
     // global tile ((bn / cyc_tpb + cyc_q0) * cyc_P + cyc_p) * cyc_tpb + bn % cyc_tpb; its offset relative to
     // cyc_row_base (global row of C row 0) is used for the lower-only test and as B's row offset.
     int cyc_P, cyc_p, cyc_tpb, cyc_q0, cyc_row_base;
+    int cyc_snake;              // block -> rank map: 0 plain cyclic (q*P + p), 1 boustrophedon (see gpx_cyc_global)
     int cyc_b_rows;             // 1: the mapped position is also B's row offset (trailing update); 0: B uses the local column
 };
+// ---- block -> rank maps of the multi-GPU layout.  Plain block-cyclic gives rank 0 the longest columns of a triangular
+// matrix (9 % more work than rank 7 at N = 65536, nb = 256, P = 8); the boustrophedon ("snake") order 0..P-1, P-1..0, ...
+// pairs a long column with a short one on every rank and balances the triangular work to second order.
+__host__ __device__ inline int64_t gpx_cyc_global(int64_t q, int P, int p, int snake) {   // global block of local block q
+    if (!snake) return q * P + p;
+    return (q >> 1) * 2 * P + ((q & 1) ? 2 * P - 1 - p : p);
+}
+__host__ __device__ inline int gpx_cyc_owner(int64_t j, int P, int snake) {
+    if (!snake) return (int)(j % P);
+    const int pos = (int)(j % (2 * P));
+    return pos < P ? pos : 2 * P - 1 - pos;
+}
+__host__ __device__ inline int64_t gpx_cyc_local(int64_t j, int P, int snake) {            // local index of block j on its owner
+    if (!snake) return j / P;
+    return 2 * (j / (2 * P)) + ((j % (2 * P)) >= P ? 1 : 0);
+}
+__host__ __device__ inline int64_t gpx_cyc_count_below(int64_t j, int P, int p, int snake) {   // # local blocks with global index < j
+    if (j <= 0) return 0;
+    if (!snake) return j > p ? (j - p + P - 1) / P : 0;
+    const int64_t cyc = j / (2 * P), rem = j % (2 * P);
+    return 2 * cyc + (rem > p ? 1 : 0) + (rem > 2 * P - 1 - p ? 1 : 0);
+}
+
 int gpx_gemm_launch(gpx_ctx* h, const GemmArgs& a);
 int gpx_gemm_tma_try_launch(gpx_ctx* h, const GemmArgs& a, double flops_exec);
 
@@ -118,9 +142,9 @@ int gpx_potrf_block(gpx_ctx* h, double* A, int64_t n, int64_t lda, double* dinv,
 int gpx_trsm_right_lt_block(gpx_ctx* h, double* B, int64_t m, int64_t ldb, const double* L, int64_t n, int64_t ldl,
                             const double* dinv);
 int gpx_trsm_left_prefix_block(gpx_ctx* h, const double* L, int64_t n, int64_t ldl, const double* dinv, double* B, int64_t ldb,
-                               int P, int p, int nb);
+                               int P, int p, int nb, int snake);
 int gpx_trsm_left_prefix_trans_block(gpx_ctx* h, const double* L, int64_t n, int64_t ldl, const double* dinv, double* B,
-                                     int64_t ldb, int P, int p, int nb);
+                                     int64_t ldb, int P, int p, int nb, int snake);
 int gpx_scratch(gpx_ctx* h, size_t bytes, void** out);
 int gpx_scratch2(gpx_ctx* h, size_t bytes, void** out);
 int gpx_read_info(gpx_ctx* h, int* info_host);

@@ -69,7 +69,7 @@ __device__ __forceinline__ int mapped_pos(const GemmArgs& p, int col0) {
     if (p.cyc_P <= 0) return col0;
     const int bw = p.cyc_tpb * 128;  // block width in elements
     const int lb = col0 / bw;
-    return ((lb + p.cyc_q0) * p.cyc_P + p.cyc_p) * bw + col0 % bw - p.cyc_row_base;
+    return (int)gpx_cyc_global(lb + p.cyc_q0, p.cyc_P, p.cyc_p, p.cyc_snake) * bw + col0 % bw - p.cyc_row_base;
 }
 
 template <bool A_KM, bool B_KM, int TN>
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(Cfg<TN>::NT, Cfg<TN>::MIN_CTAS) dgemm_dmma_ker
 int host_mapped_pos(const GemmArgs& a, int col0) {
     if (a.cyc_P <= 0) return col0;
     const int bw = a.cyc_tpb * 128;
-    return ((col0 / bw + a.cyc_q0) * a.cyc_P + a.cyc_p) * bw + col0 % bw - a.cyc_row_base;
+    return (int)gpx_cyc_global(col0 / bw + a.cyc_q0, a.cyc_P, a.cyc_p, a.cyc_snake) * bw + col0 % bw - a.cyc_row_base;
 }
 
 // flops a launch really executes (tile-granular k ranges), for the instrumentation

@@ -74,7 +74,7 @@ __device__ __forceinline__ int mapped_pos(const GemmArgs& p, int col0) {
     if (p.cyc_P <= 0) return col0;
     const int bw = p.cyc_tpb * 128;
     const int lb = col0 / bw;
-    return ((lb + p.cyc_q0) * p.cyc_P + p.cyc_p) * bw + col0 % bw - p.cyc_row_base;
+    return (int)gpx_cyc_global(lb + p.cyc_q0, p.cyc_P, p.cyc_p, p.cyc_snake) * bw + col0 % bw - p.cyc_row_base;
 }
 
 __device__ __forceinline__ int rho8(int g) { return (g & 1) | (((g >> 1) & 1) << 2) | ((g >> 2) << 1); }

@@ -86,8 +86,8 @@ struct MgBuild {            // what matrix is factored: scale_i k(x_i, x_j; thet
 
 struct MgRank {
     gpx_ctx* h;         // handle whose stream the rank's kernels run on
-    int P, p;           // world, rank
-    int64_t n, npad;    // true / padded size (npad % (nb*P) == 0)
+    int P, p, snake;    // world, rank, block -> rank map (gpx_cyc_*)
+    int64_t n, npad;    // true / padded size (npad % (nb*P) == 0; nb*2P with the snake map)
     int nb, tpb, G;     // block width, tiles per block, panels per group (bulk K = G*nb)
     int64_t nblk, nloc, wloc;   // global blocks, local blocks, local width (elements)
     double *Aloc, *Xloc, *Lfull, *dinv, *stage[2], *vec, *solve_ws;
@@ -103,12 +103,21 @@ int group_k() {   // K of the grouped bulk update
     return g_group_k;
 }
 
-__global__ void set_identity_blocks_kernel(double* X, int64_t ld, int64_t nloc, int nb, int P, int p) {
-    // X[(q*P+p)*nb + i][q*nb + i] = 1 for every local block q
+int g_snake = -1;
+int layout_snake() {   // 1: boustrophedon block -> rank map (default), 0: plain block-cyclic
+    if (g_snake < 0) {
+        const char* e = getenv("GPX_MG_SNAKE");
+        g_snake = e ? (atoi(e) != 0) : 1;
+    }
+    return g_snake;
+}
+
+__global__ void set_identity_blocks_kernel(double* X, int64_t ld, int64_t nloc, int nb, int P, int p, int snake) {
+    // X[global(q)*nb + i][q*nb + i] = 1 for every local block q
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nloc * nb) return;
     int64_t q = idx / nb, i = idx - q * nb;
-    X[((q * P + p) * nb + i) * ld + q * nb + i] = 1.0;
+    X[(gpx_cyc_global(q, P, p, snake) * nb + i) * ld + q * nb + i] = 1.0;
 }
 
 size_t stage_elems(int64_t npad, int nb) { return (size_t)npad * nb + (size_t)(nb / GPX_T) * GPX_T * GPX_T; }
@@ -120,7 +129,7 @@ size_t solve_ws_elems(int64_t npad) {
 // owner side: factor diagonal block j and TRSM the panel below it (in Aloc), then pack panel + leaf inverses
 int panel_factor_pack(MgRank& r, int64_t j, double* stage) {
     gpx_ctx* h = r.h;
-    const int64_t q = j / r.P, r0 = j * r.nb, rows = r.npad - r0;
+    const int64_t q = gpx_cyc_local(j, r.P, r.snake), r0 = j * r.nb, rows = r.npad - r0;
     double* diag = r.Aloc + r0 * r.wloc + q * r.nb;
     double* dinvj = r.dinv + j * r.tpb * GPX_T * GPX_T;
     GPX_TRY(gpx_potrf_block(h, diag, r.nb, r.wloc, dinvj, (int)r0));
@@ -148,7 +157,7 @@ int panel_unpack(MgRank& r, int64_t j, const double* stage, cudaStream_t s) {
 int trailing_update(MgRank& r, int64_t j_lo, int np_panels, int64_t q_lo, int64_t q_hi) {
     if (q_hi > r.nloc) q_hi = r.nloc;
     if (q_lo >= q_hi || np_panels <= 0) return 0;
-    const int64_t gk0 = q_lo * r.P + r.p;            // global block of the first updated local column
+    const int64_t gk0 = gpx_cyc_global(q_lo, r.P, r.p, r.snake);   // global block of the first updated local column
     const int64_t r_start = gk0 * r.nb;
     GemmArgs a{};
     a.batch = 1;
@@ -158,14 +167,14 @@ int trailing_update(MgRank& r, int64_t j_lo, int np_panels, int64_t q_lo, int64_
     a.C = r.Aloc + r_start * r.wloc + q_lo * r.nb; a.ldc = r.wloc;
     a.M = (int)(r.npad - r_start); a.N = (int)((q_hi - q_lo) * r.nb); a.K = np_panels * r.nb;
     a.lower_only = 1;
-    a.cyc_P = r.P; a.cyc_p = r.p; a.cyc_tpb = r.tpb; a.cyc_q0 = (int)q_lo; a.cyc_row_base = (int)r_start; a.cyc_b_rows = 1;
+    a.cyc_P = r.P; a.cyc_p = r.p; a.cyc_snake = r.snake; a.cyc_tpb = r.tpb; a.cyc_q0 = (int)q_lo; a.cyc_row_base = (int)r_start; a.cyc_b_rows = 1;
     return gpx_gemm_launch(r.h, a);
 }
 
-int64_t first_local_block_after(const MgRank& r, int64_t j) {  // smallest q with q*P + p > j
-    if (j < r.p) return 0;
-    return (j - r.p) / r.P + 1;
+int64_t first_local_block_after(const MgRank& r, int64_t j) {  // smallest local q whose global block is > j
+    return gpx_cyc_count_below(j + 1, r.P, r.p, r.snake);
 }
+int owner_of(const MgRank& r, int64_t j) { return gpx_cyc_owner(j, r.P, r.snake); }
 
 // Deferred bulk update B(g): the panels of group g applied to the local columns beyond group g+1, cut into `nchunks`
 // column ranges of roughly equal area; chunk c is issued at step c of the next group.
@@ -185,11 +194,11 @@ BulkPlan plan_bulk(const MgRank& r, int64_t g, int nchunks) {
     if (nchunks <= 0 || q_lo >= r.nloc) return bp;
     // area of column q ~ rows below its diagonal block
     double total = 0.0;
-    for (int64_t q = q_lo; q < r.nloc; ++q) total += (double)(r.nblk - (q * r.P + r.p));
+    for (int64_t q = q_lo; q < r.nloc; ++q) total += (double)(r.nblk - gpx_cyc_global(q, r.P, r.p, r.snake));
     double acc = 0.0;
     int c = 1;
     for (int64_t q = q_lo; q < r.nloc && c < nchunks; ++q) {
-        acc += (double)(r.nblk - (q * r.P + r.p));
+        acc += (double)(r.nblk - gpx_cyc_global(q, r.P, r.p, r.snake));
         if (acc >= total * c / nchunks) bp.q_cut[c++] = q + 1;
     }
     for (; c < nchunks; ++c) bp.q_cut[c] = r.nloc;
@@ -211,7 +220,7 @@ int rank_step(MgRank& r, int64_t j, double* next_stage, OnPanel&& on_panel) {
     const int gw = (int)std::min<int64_t>(r.G, r.nblk - j0);
     const int64_t jl = j0 + gw - 1;                       // last panel of the group
     const int64_t qa = first_local_block_after(r, j), qe = first_local_block_after(r, jl);
-    if (j < jl && (int)((j + 1) % r.P) == r.p) {          // the next panel of this group is mine: it is local block qa
+    if (j < jl && owner_of(r, j + 1) == r.p) {             // the next panel of this group is mine: it is local block qa
         GPX_TRY(trailing_update(r, j, 1, qa, qa + 1));
         GPX_TRY(panel_factor_pack(r, j + 1, next_stage));
         GPX_TRY(on_panel(j + 1, next_stage));
@@ -222,7 +231,7 @@ int rank_step(MgRank& r, int64_t j, double* next_stage, OnPanel&& on_panel) {
     if (j == jl && jl + 1 < r.nblk) {                     // group complete: A(g) on the next group's columns
         const int64_t qn = first_local_block_after(r, jl + r.G);
         GPX_TRY(trailing_update(r, j0, gw, qe, qn));
-        if ((int)((jl + 1) % r.P) == r.p) {
+        if (owner_of(r, jl + 1) == r.p) {
             GPX_TRY(panel_factor_pack(r, jl + 1, next_stage));
             GPX_TRY(on_panel(jl + 1, next_stage));
         }
@@ -232,7 +241,7 @@ int rank_step(MgRank& r, int64_t j, double* next_stage, OnPanel&& on_panel) {
 
 int build_local(MgRank& r, const MgBuild& b) {
     for (int64_t q = 0; q < r.nloc; ++q) {
-        const int64_t j = q * r.P + r.p;
+        const int64_t j = gpx_cyc_global(q, r.P, r.p, r.snake);
         GPX_TRY(gpx_cov_build_block(r.h, b.kind, b.X, b.n, b.D, b.theta, b.ntheta, b.diag_add, GPX_COV_SAME_X | GPX_COV_LOWER,
                                     r.Aloc + q * r.nb, r.npad, r.nb, r.wloc, 0, (int)(j * r.nb), b.scale));
     }
@@ -247,7 +256,7 @@ __global__ void accumulate_kernel(int n, const double* __restrict__ x, double* _
 int grad_local(MgRank& r, int kind, const double* X, int D, const double* theta, int ntheta, const double* alpha,
                double* grad_acc /* device, ntheta, zeroed by caller */, double* tmp /* device, ntheta */) {
     for (int64_t q = 0; q < r.nloc; ++q) {
-        const int64_t j = q * r.P + r.p, r0 = j * r.nb;
+        const int64_t j = gpx_cyc_global(q, r.P, r.p, r.snake), r0 = j * r.nb;
         GPX_TRY(gpx_lml_grad_block(r.h, kind, X, r.n, D, theta, ntheta, r.Xloc + r0 * r.wloc + q * r.nb, r.wloc, alpha, tmp,
                                    r.npad - r0, r.nb, (int)r0, (int)r0));
         accumulate_kernel<<<1, 32, 0, r.h->stream>>>(ntheta, tmp, grad_acc);
@@ -260,12 +269,12 @@ int grad_local(MgRank& r, int kind, const double* X, int D, const double* theta,
 int inverse_local(MgRank& r) {
     GPX_CUDA(cudaMemsetAsync(r.Xloc, 0, (size_t)r.npad * r.wloc * sizeof(double), r.h->stream));
     const int64_t cnt = r.nloc * r.nb;
-    set_identity_blocks_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, r.h->stream>>>(r.Xloc, r.wloc, r.nloc, r.nb, r.P, r.p);
+    set_identity_blocks_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, r.h->stream>>>(r.Xloc, r.wloc, r.nloc, r.nb, r.P, r.p, r.snake);
     GPX_CHECK_LAUNCH(r.h);
     gpx_phase_mark(r.h, GPX_PH_TRTRI);
-    GPX_TRY(gpx_trsm_left_prefix_block(r.h, r.Lfull, r.npad, r.npad, r.dinv, r.Xloc, r.wloc, r.P, r.p, r.nb));        // X = L^-1 E
+    GPX_TRY(gpx_trsm_left_prefix_block(r.h, r.Lfull, r.npad, r.npad, r.dinv, r.Xloc, r.wloc, r.P, r.p, r.nb, r.snake));   // X = L^-1 E
     gpx_phase_mark(r.h, GPX_PH_LAUUM);
-    return gpx_trsm_left_prefix_trans_block(r.h, r.Lfull, r.npad, r.npad, r.dinv, r.Xloc, r.wloc, r.P, r.p, r.nb);    // Z = L^-T X
+    return gpx_trsm_left_prefix_trans_block(r.h, r.Lfull, r.npad, r.npad, r.dinv, r.Xloc, r.wloc, r.P, r.p, r.nb, r.snake);    // Z = L^-T X
 }
 
 // alpha = L^-T L^-1 y and {lml, y.alpha, sum log diag} on the replicated factor (short-chain blocked TRSVs)
@@ -291,8 +300,8 @@ int solve_lml(MgRank& r, const double* y, double* alpha, double* out3) {
 int init_rank(MgRank& r, gpx_ctx* h, int P, int p, int64_t n, int nb, double* ws) {
     r.h = h; r.P = P; r.p = p; r.n = n; r.nb = nb; r.tpb = nb / GPX_T;
     r.G = std::max(1, group_k() / nb);
-    const int64_t unit = (int64_t)nb * P;
-    r.npad = ((n + unit - 1) / unit) * unit;
+    r.snake = layout_snake();
+    r.npad = gpx_mg_padded_dim(n, nb, P);
     r.nblk = r.npad / nb; r.nloc = r.nblk / P; r.wloc = r.nloc * nb;
     double* w = ws;
     r.Aloc = w; w += (size_t)r.npad * r.wloc;
@@ -335,7 +344,7 @@ int factor_rank(MgRank& r, const MgBuild& b, int* info_out) {
         bool have_prev = false;
         for (int64_t j = 0; j < r.nblk; ++j) {
             const int sb = (int)(j & 1);
-            const int owner = (int)(j % P);
+            const int owner = owner_of(r, j);
             const int64_t rows = r.npad - j * r.nb;
             const size_t count = (size_t)rows * r.nb + (size_t)r.tpb * GPX_T * GPX_T;
             const int64_t g = j / r.G, j0 = g * r.G;
@@ -345,14 +354,19 @@ int factor_rank(MgRank& r, const MgBuild& b, int* info_out) {
             // (running in lock-step) is about to finish the panel: a receive kernel launched earlier would spin on
             // ~20 SMs' worth of registers for a whole step and slow the bulk GEMM by ~14 % (measured at 2 GPUs).
             GPX_CUDA(cudaStreamWaitEvent(Cs, evPanel[sb], 0));
-            if (P > 1) GPX_NCCL(g_nccl.Broadcast(r.stage[sb], r.stage[sb], count, NCCL_F64, owner, (ncclComm_p)h->nccl_comm, Cs));
+            if (P > 1) {
+                // a one-element broadcast first: its single-CTA kernel is what spins until the owner is ready, so the
+                // many-channel kernel of the panel itself starts when the data is there and never idles on the SMs
+                GPX_NCCL(g_nccl.Broadcast(r.vec, r.vec, 1, NCCL_F64, owner, (ncclComm_p)h->nccl_comm, Cs));
+                GPX_NCCL(g_nccl.Broadcast(r.stage[sb], r.stage[sb], count, NCCL_F64, owner, (ncclComm_p)h->nccl_comm, Cs));
+            }
             GPX_TRY(panel_unpack(r, j, r.stage[sb], Cs));
             GPX_CUDA(cudaEventRecord(evRecv[sb], Cs));
             // ---- compute stream: the deferred chunk does not need panel j, so it is issued BEFORE the wait
             if (have_prev) GPX_TRY(bulk_chunk(r, prev, (int)(j - j0)));
             GPX_CUDA(cudaStreamWaitEvent(S, evRecv[sb], 0));
             GPX_TRY(rank_step(r, j, r.stage[sb ^ 1], on_panel));
-            if (j + 1 < r.nblk && (int)((j + 1) % P) != r.p) GPX_CUDA(cudaEventRecord(evPanel[sb ^ 1], S));   // the gate above
+            if (j + 1 < r.nblk && owner_of(r, j + 1) != r.p) GPX_CUDA(cudaEventRecord(evPanel[sb ^ 1], S));   // the gate above
             if (j == j0 + gw - 1) {   // group complete: its bulk update is deferred into the steps of the next group
                 const int64_t jn0 = j0 + gw;
                 const int gw_next = jn0 < r.nblk ? (int)std::min<int64_t>(r.G, r.nblk - jn0) : 0;
@@ -398,8 +412,20 @@ extern "C" int gpx_mg_set_group_k(int k) {
 }
 
 extern "C" int64_t gpx_mg_padded_dim(int64_t n, int nb, int world) {
-    const int64_t unit = (int64_t)nb * world;
+    const int64_t unit = (int64_t)nb * world * (layout_snake() ? 2 : 1);   // every rank owns the same number of blocks
     return ((n + unit - 1) / unit) * unit;
+}
+
+// the map itself (host-side queries; no GPU needed): owner of global block j, global block of local block q on rank p,
+// number of rank p's blocks with global index < j
+extern "C" int gpx_mg_block_owner(int64_t j, int world) { return gpx_cyc_owner(j, world, layout_snake()); }
+extern "C" int64_t gpx_mg_block_global(int64_t q, int world, int rank) { return gpx_cyc_global(q, world, rank, layout_snake()); }
+extern "C" int64_t gpx_mg_blocks_below(int64_t j, int world, int rank) { return gpx_cyc_count_below(j, world, rank, layout_snake()); }
+
+// block -> rank map of the multi-GPU layout: 1 = boustrophedon (default, balances the triangular work), 0 = plain cyclic
+extern "C" int gpx_mg_set_layout(int snake) {
+    g_snake = snake ? 1 : 0;
+    return 0;
 }
 
 // doubles of device workspace one rank needs for the gpx_mg_* calls
@@ -597,7 +623,7 @@ extern "C" int gpx_mg_emulate_fit_grad(gpx_handle h, int P, int kind, const doub
     bool have_prev = false;
     for (int64_t j = 0; j < r0.nblk; ++j) {
         const int sb = (int)(j & 1);
-        const int owner = (int)(j % P);
+        const int owner = owner_of(r0, j);
         const int64_t rows = r0.npad - j * r0.nb;
         const size_t count = (size_t)rows * r0.nb + (size_t)r0.tpb * GPX_T * GPX_T;
         const int64_t g = j / r0.G, j0 = g * r0.G;

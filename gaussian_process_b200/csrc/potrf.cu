@@ -769,12 +769,11 @@ namespace {
 // Left lower TRSM  L X = B  where only a *prefix* of B's columns is non-zero in any given row range: for rows
 // below global row r (relative to this sub-problem's row 0 at global row `grow0`), the non-zero columns are the
 // local blocks whose global block index is <= block(r): count = prefix(r).  Used for L^-1 on block-cyclic columns.
-struct PrefixMap { int P, p, nb; };
+struct PrefixMap { int P, p, nb, snake; };
 inline int64_t prefix_cols(const PrefixMap& pm, int64_t grow_end) {
     // number of local columns (elements) whose global block start is < grow_end
     const int64_t nblk_below = (grow_end + pm.nb - 1) / pm.nb;              // global blocks 0..nblk_below-1 start below grow_end
-    const int64_t cnt = nblk_below > pm.p ? (nblk_below - pm.p + pm.P - 1) / pm.P : 0;  // those owned by rank p
-    return cnt * pm.nb;
+    return gpx_cyc_count_below(nblk_below, pm.P, pm.p, pm.snake) * pm.nb;   // those owned by rank p
 }
 int trsm_left_prefix(gpx_ctx* h, const double* L, int64_t n, int64_t ldl, const double* dinv, double* B, int64_t ldb,
                      int64_t grow0, const PrefixMap& pm) {
@@ -799,7 +798,7 @@ int trsm_left_prefix(gpx_ctx* h, const double* L, int64_t n, int64_t ldl, const 
         a.M = (int)h2; a.N = (int)nc1; a.K = (int)h1;
         a.alpha = -1.0; a.beta = 1.0;
         // X1[k][c] is zero for global rows above the start of c's block: begin the k loop there
-        a.kb_mode = 3; a.cyc_P = pm.P; a.cyc_p = pm.p; a.cyc_tpb = pm.nb / LT; a.cyc_q0 = 0; a.cyc_row_base = (int)grow0;
+        a.kb_mode = 3; a.cyc_P = pm.P; a.cyc_p = pm.p; a.cyc_snake = pm.snake; a.cyc_tpb = pm.nb / LT; a.cyc_q0 = 0; a.cyc_row_base = (int)grow0;
         a.cyc_b_rows = 0;
         GPX_TRY(gpx_gemm_launch(h, a));
     }
@@ -808,8 +807,8 @@ int trsm_left_prefix(gpx_ctx* h, const double* L, int64_t n, int64_t ldl, const 
 }  // namespace
 
 int gpx_trsm_left_prefix_block(gpx_ctx* h, const double* L, int64_t n, int64_t ldl, const double* dinv, double* B, int64_t ldb,
-                               int P, int p, int nb) {
-    PrefixMap pm{P, p, nb};
+                               int P, int p, int nb, int snake) {
+    PrefixMap pm{P, p, nb, snake};
     return trsm_left_prefix(h, L, n, ldl, dinv, B, ldb, 0, pm);
 }
 
@@ -842,7 +841,7 @@ int trsm_left_prefix_trans(gpx_ctx* h, const double* L, int64_t n, int64_t ldl, 
         a.M = (int)h1; a.N = (int)nc1; a.K = (int)h2;
         a.alpha = -1.0; a.beta = 1.0;
         a.lower_only = 1;   // rows above a column's block start are never needed
-        a.cyc_P = pm.P; a.cyc_p = pm.p; a.cyc_tpb = pm.nb / LT; a.cyc_q0 = 0; a.cyc_row_base = (int)grow0; a.cyc_b_rows = 0;
+        a.cyc_P = pm.P; a.cyc_p = pm.p; a.cyc_snake = pm.snake; a.cyc_tpb = pm.nb / LT; a.cyc_q0 = 0; a.cyc_row_base = (int)grow0; a.cyc_b_rows = 0;
         GPX_TRY(gpx_gemm_launch(h, a));
     }
     return trsm_left_prefix_trans(h, L, h1, ldl, dinv, B, ldb, grow0, pm);
@@ -850,8 +849,8 @@ int trsm_left_prefix_trans(gpx_ctx* h, const double* L, int64_t n, int64_t ldl, 
 }  // namespace
 
 int gpx_trsm_left_prefix_trans_block(gpx_ctx* h, const double* L, int64_t n, int64_t ldl, const double* dinv, double* B,
-                                     int64_t ldb, int P, int p, int nb) {
-    PrefixMap pm{P, p, nb};
+                                     int64_t ldb, int P, int p, int nb, int snake) {
+    PrefixMap pm{P, p, nb, snake};
     return trsm_left_prefix_trans(h, L, n, ldl, dinv, B, ldb, 0, pm);
 }
 

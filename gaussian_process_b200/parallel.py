@@ -11,38 +11,55 @@ import numpy as np
 
 
 # ---- 1-D block-cyclic layout of block columns (the P x 1 case of the 2-D block-cyclic scheme) ----------------
-def mg_padded_dim(n: int, nb: int, world: int) -> int:
-    unit = nb * world
+# Two block -> rank maps (csrc/common.cuh gpx_cyc_*): plain cyclic (j mod P) and the default boustrophedon ("snake")
+# order 0..P-1, P-1..0, 0.. which pairs a long column of the triangular matrix with a short one on every rank.
+def mg_padded_dim(n: int, nb: int, world: int, snake: bool = True) -> int:
+    unit = nb * world * (2 if snake else 1)
     return ((n + unit - 1) // unit) * unit
 
 
-def owner_of_block(j: int, world: int) -> int:
-    return j % world
+def owner_of_block(j: int, world: int, snake: bool = True) -> int:
+    if not snake:
+        return j % world
+    pos = j % (2 * world)
+    return pos if pos < world else 2 * world - 1 - pos
 
 
-def local_index_of_block(j: int, world: int) -> int:
-    return j // world
+def local_index_of_block(j: int, world: int, snake: bool = True) -> int:
+    if not snake:
+        return j // world
+    return 2 * (j // (2 * world)) + (1 if j % (2 * world) >= world else 0)
 
 
-def global_block(q: int, rank: int, world: int) -> int:
-    return q * world + rank
+def global_block(q: int, rank: int, world: int, snake: bool = True) -> int:
+    if not snake:
+        return q * world + rank
+    return (q // 2) * 2 * world + (2 * world - 1 - rank if q % 2 else rank)
 
 
-def local_blocks(nblk: int, rank: int, world: int) -> List[int]:
+def local_blocks(nblk: int, rank: int, world: int, snake: bool = True) -> List[int]:
     """Global block indices owned by ``rank``."""
-    return list(range(rank, nblk, world))
+    return [j for j in range(nblk) if owner_of_block(j, world, snake) == rank]
 
 
-def first_local_block_after(j: int, rank: int, world: int) -> int:
-    """Smallest local index q whose global block q*world+rank is > j (trailing-update range)."""
-    return 0 if j < rank else (j - rank) // world + 1
+def blocks_below(j: int, rank: int, world: int, snake: bool = True) -> int:
+    """Number of the rank's blocks with global index < j."""
+    if j <= 0:
+        return 0
+    if not snake:
+        return (j - rank + world - 1) // world if j > rank else 0
+    cyc, rem = divmod(j, 2 * world)
+    return 2 * cyc + (1 if rem > rank else 0) + (1 if rem > 2 * world - 1 - rank else 0)
 
 
-def prefix_cols(grow_end: int, nb: int, rank: int, world: int) -> int:
+def first_local_block_after(j: int, rank: int, world: int, snake: bool = True) -> int:
+    """Smallest local index q whose global block is > j (trailing-update range)."""
+    return blocks_below(j + 1, rank, world, snake)
+
+
+def prefix_cols(grow_end: int, nb: int, rank: int, world: int, snake: bool = True) -> int:
     """Number of local columns whose global block starts below row ``grow_end`` (structure of L^-1's columns)."""
-    nblk_below = (grow_end + nb - 1) // nb
-    cnt = (nblk_below - rank + world - 1) // world if nblk_below > rank else 0
-    return cnt * nb
+    return blocks_below((grow_end + nb - 1) // nb, rank, world, snake) * nb
 
 
 # ---- sharding of independent work ---------------------------------------------------------------------------

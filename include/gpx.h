@@ -241,7 +241,11 @@ int     gpx_nccl_load(const char* libnccl_path);                        /* optio
 int     gpx_nccl_unique_id(void* id128);                                /* rank 0: fills 128 bytes */
 int     gpx_nccl_init(gpx_handle h, const void* id128, int rank, int world);
 int     gpx_mg_set_group_k(int k);                                      /* K of the grouped trailing update (default 1024) */
-int64_t gpx_mg_padded_dim(int64_t n, int nb, int world);                /* n rounded up to nb*world */
+int     gpx_mg_set_layout(int snake);                                   /* 1 (default): boustrophedon block->rank map; 0: plain block-cyclic */
+int     gpx_mg_block_owner(int64_t j, int world);                       /* rank that owns global block column j */
+int64_t gpx_mg_block_global(int64_t q, int world, int rank);            /* global block of local block q */
+int64_t gpx_mg_blocks_below(int64_t j, int world, int rank);            /* # of the rank's blocks with global index < j */
+int64_t gpx_mg_padded_dim(int64_t n, int nb, int world);                /* n rounded up to nb*world (2*nb*world with the default map) */
 int64_t gpx_mg_workspace_elems(int64_t n, int nb, int world);           /* doubles of device workspace per rank */
 /* Element offsets of the pieces inside the workspace: out6 = {Aloc, Kloc (local block columns of K^-1 after a fit with
  * gradient; rows on/below each block's diagonal block are valid), Lfull (replicated factor: npad x npad row-major, clean lower

@@ -51,6 +51,20 @@ def test_emulated_ranks_group_sizes(eng, group_k):
     assert rel(lml, lml_o) < 1e-8 and rel(alpha, alpha_o) < 1e-7 and rel(grad[1], grad_o) < 1e-7
 
 
+@pytest.mark.parametrize("P,nb,n", [(2, 128, 900), (3, 128, 1000), (8, 128, 2100)])
+def test_emulated_ranks_plain_cyclic_map(eng, P, nb, n):
+    """The plain block-cyclic map (gpx_mg_set_layout(0)) stays supported next to the default boustrophedon map."""
+    from gaussian_process_b200._lib import COV_SE, check
+    X, y = O.synth_c5(n, 16)
+    check(eng.lib.gpx_mg_set_layout(0), "gpx_mg_set_layout")
+    try:
+        lml, grad, alpha = eng.mg_emulate_fit_grad(P, COV_SE, X, y, [1.0, 4.0], 5e-4, nb=nb)
+    finally:
+        check(eng.lib.gpx_mg_set_layout(1), "gpx_mg_set_layout")
+    lml_o, grad_o, alpha_o = O.rbf_fit_lml_grad(X, y, 1.0, 4.0)
+    assert rel(lml, lml_o) < 1e-8 and rel(alpha, alpha_o) < 1e-7 and rel(grad[1], grad_o) < 1e-7
+
+
 def test_emulated_ranks_co2_all_theta(eng):
     from gaussian_process_b200._lib import COV_CO2
     X, y, _ = O.synth_c2(500)

@@ -12,31 +12,69 @@ import torch.multiprocessing as mp
 from gaussian_process_b200 import parallel as P
 
 
-def test_block_cyclic_maps_are_consistent():
+@pytest.mark.parametrize("snake", [True, False])
+def test_block_cyclic_maps_are_consistent(snake):
     for world in (1, 2, 3, 8):
-        nblk = 5 * world
+        nblk = 6 * world
         seen = []
         for r in range(world):
-            blocks = P.local_blocks(nblk, r, world)
+            blocks = P.local_blocks(nblk, r, world, snake)
+            assert len(blocks) == nblk // world                      # every rank owns the same number of blocks
             for q, j in enumerate(blocks):
-                assert P.owner_of_block(j, world) == r and P.local_index_of_block(j, world) == q
-                assert P.global_block(q, r, world) == j
+                assert P.owner_of_block(j, world, snake) == r and P.local_index_of_block(j, world, snake) == q
+                assert P.global_block(q, r, world, snake) == j
             seen += blocks
         assert sorted(seen) == list(range(nblk))
         for r in range(world):
             for j in range(nblk):
-                q = P.first_local_block_after(j, r, world)
-                assert q == len([b for b in P.local_blocks(nblk, r, world) if b <= j])
-    assert P.mg_padded_dim(65536, 512, 8) == 65536 and P.mg_padded_dim(1000, 256, 3) == 1536
+                q = P.first_local_block_after(j, r, world, snake)
+                assert q == len([b for b in P.local_blocks(nblk, r, world, snake) if b <= j])
+    assert P.mg_padded_dim(65536, 512, 8, snake) == 65536
+    assert P.mg_padded_dim(1000, 256, 3, False) == 1536 and P.mg_padded_dim(1000, 256, 3, True) == 1536
+    assert P.mg_padded_dim(1600, 256, 3, True) == 3072
 
 
-def test_prefix_cols_matches_brute_force():
+def test_snake_map_balances_triangular_work():
+    """Work of a column of a lower-triangular matrix ~ (rows below it)^2: plain cyclic gives rank 0 ~9 % more than rank 7 at
+    N = 65536, nb = 256, P = 8; the boustrophedon map brings the spread to 0.25 %."""
+    nblk, world = 256, 8
+    for snake, bound in ((False, 0.05), (True, 0.005)):
+        w = [sum((nblk - j) ** 2 for j in P.local_blocks(nblk, r, world, snake)) for r in range(world)]
+        spread = (max(w) - min(w)) / (sum(w) / world)
+        assert (spread > bound) if not snake else (spread < bound), (snake, spread)
+
+
+@pytest.mark.parametrize("snake", [True, False])
+def test_library_block_maps_match_the_python_mirror(snake):
+    """The C maps the kernels use (gpx_mg_block_*; no GPU needed) against gaussian_process_b200.parallel."""
+    from gaussian_process_b200 import _lib
+    if not os.path.isfile(_lib.LIB_PATH):
+        pytest.skip("libgpx.so not built")
+    lib = _lib.load()
+    lib.gpx_mg_set_layout(int(snake))
+    try:
+        for world in (1, 2, 3, 8):
+            for j in range(0, 7 * world):
+                assert lib.gpx_mg_block_owner(j, world) == P.owner_of_block(j, world, snake)
+                for r in range(world):
+                    assert lib.gpx_mg_blocks_below(j, world, r) == P.blocks_below(j, r, world, snake)
+            for r in range(world):
+                for q in range(9):
+                    assert lib.gpx_mg_block_global(q, world, r) == P.global_block(q, r, world, snake)
+            assert lib.gpx_mg_padded_dim(1000, 256, world) == P.mg_padded_dim(1000, 256, world, snake)
+    finally:
+        lib.gpx_mg_set_layout(1)
+
+
+@pytest.mark.parametrize("snake", [True, False])
+def test_prefix_cols_matches_brute_force(snake):
     nb = 256
     for world in (1, 2, 4):
         for rank in range(world):
+            owned = P.local_blocks(64, rank, world, snake)
             for grow_end in range(0, 10 * nb + 1, 128):
-                brute = sum(nb for j in range(rank, 64, world) if j * nb < grow_end)
-                assert P.prefix_cols(grow_end, nb, rank, world) == brute
+                brute = sum(nb for j in owned if j * nb < grow_end)
+                assert P.prefix_cols(grow_end, nb, rank, world, snake) == brute
 
 
 def test_sharding_partitions():
