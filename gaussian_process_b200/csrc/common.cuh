@@ -142,9 +142,10 @@ int gpx_potrf_block(gpx_ctx* h, double* A, int64_t n, int64_t lda, double* dinv,
 int gpx_trsm_right_lt_block(gpx_ctx* h, double* B, int64_t m, int64_t ldb, const double* L, int64_t n, int64_t ldl,
                             const double* dinv);
 int gpx_trsm_left_prefix_block(gpx_ctx* h, const double* L, int64_t n, int64_t ldl, const double* dinv, double* B, int64_t ldb,
-                               int P, int p, int nb, int snake);
+                               int P, int p, int nb, int snake, const double* D = nullptr, int bs = 0, double* tmp = nullptr);
 int gpx_trsm_left_prefix_trans_block(gpx_ctx* h, const double* L, int64_t n, int64_t ldl, const double* dinv, double* B,
-                                     int64_t ldb, int P, int p, int nb, int snake);
+                                     int64_t ldb, int P, int p, int nb, int snake, const double* D = nullptr, int bs = 0,
+                                     double* tmp = nullptr);
 int gpx_scratch(gpx_ctx* h, size_t bytes, void** out);
 int gpx_scratch2(gpx_ctx* h, size_t bytes, void** out);
 int gpx_read_info(gpx_ctx* h, int* info_host);

@@ -90,7 +90,7 @@ struct MgRank {
     int64_t n, npad;    // true / padded size (npad % (nb*P) == 0; nb*2P with the snake map)
     int nb, tpb, G;     // block width, tiles per block, panels per group (bulk K = G*nb)
     int64_t nblk, nloc, wloc;   // global blocks, local blocks, local width (elements)
-    double *Aloc, *Xloc, *Lfull, *dinv, *stage[2], *vec, *solve_ws;
+    double *Aloc, *Xloc, *Lfull, *dinv, *stage[2], *vec, *solve_ws, *trsm_tmp;
 };
 
 int g_group_k = -1;
@@ -121,9 +121,25 @@ __global__ void set_identity_blocks_kernel(double* X, int64_t ld, int64_t nloc, 
 }
 
 size_t stage_elems(int64_t npad, int nb) { return (size_t)npad * nb + (size_t)(nb / GPX_T) * GPX_T * GPX_T; }
-size_t solve_ws_elems(int64_t npad) {
+size_t solve_ws_elems(int64_t npad) {   // block inverses (npad*bs) + their build scratch + the TRSV scratch
     const int64_t bs = gpx_block_size_for(npad);
     return (size_t)npad * bs + (size_t)npad * bs / 4 + GPX_T + bs + 64;
+}
+struct SolveWs { int bs; double *Dbig, *work, *tmp; bool use; };
+SolveWs solve_ws_of(const MgRank& r) {
+    SolveWs w;
+    w.bs = gpx_block_size_for(r.npad);
+    w.Dbig = r.solve_ws;
+    w.work = w.Dbig + (size_t)r.npad * w.bs;
+    w.tmp = w.work + (size_t)r.npad * w.bs / 4 + GPX_T;
+    w.use = w.bs > GPX_T && r.npad >= 2 * w.bs;
+    return w;
+}
+// explicit inverses of the bs x bs diagonal blocks of the replicated factor: shared by the TRSVs and the two TRSMs
+int build_block_inverses(MgRank& r) {
+    SolveWs w = solve_ws_of(r);
+    if (!w.use) return 0;
+    return gpx_block_inverses(r.h, r.Lfull, r.npad, r.npad, r.dinv, w.bs, w.Dbig, w.work);
 }
 
 // owner side: factor diagonal block j and TRSM the panel below it (in Aloc), then pack panel + leaf inverses
@@ -271,10 +287,14 @@ int inverse_local(MgRank& r) {
     const int64_t cnt = r.nloc * r.nb;
     set_identity_blocks_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, r.h->stream>>>(r.Xloc, r.wloc, r.nloc, r.nb, r.P, r.p, r.snake);
     GPX_CHECK_LAUNCH(r.h);
+    SolveWs w = solve_ws_of(r);     // block inverses must have been built (build_block_inverses)
+    const double* D = w.use ? w.Dbig : nullptr;
     gpx_phase_mark(r.h, GPX_PH_TRTRI);
-    GPX_TRY(gpx_trsm_left_prefix_block(r.h, r.Lfull, r.npad, r.npad, r.dinv, r.Xloc, r.wloc, r.P, r.p, r.nb, r.snake));   // X = L^-1 E
+    GPX_TRY(gpx_trsm_left_prefix_block(r.h, r.Lfull, r.npad, r.npad, r.dinv, r.Xloc, r.wloc, r.P, r.p, r.nb, r.snake, D, w.bs,
+                                       r.trsm_tmp));                                                                   // X = L^-1 E
     gpx_phase_mark(r.h, GPX_PH_LAUUM);
-    return gpx_trsm_left_prefix_trans_block(r.h, r.Lfull, r.npad, r.npad, r.dinv, r.Xloc, r.wloc, r.P, r.p, r.nb, r.snake);    // Z = L^-T X
+    return gpx_trsm_left_prefix_trans_block(r.h, r.Lfull, r.npad, r.npad, r.dinv, r.Xloc, r.wloc, r.P, r.p, r.nb, r.snake, D,
+                                            w.bs, r.trsm_tmp);                                                         // Z = L^-T X
 }
 
 // alpha = L^-T L^-1 y and {lml, y.alpha, sum log diag} on the replicated factor (short-chain blocked TRSVs)
@@ -282,14 +302,10 @@ int solve_lml(MgRank& r, const double* y, double* alpha, double* out3) {
     gpx_ctx* h = r.h;
     GPX_CUDA(cudaMemsetAsync(alpha, 0, r.npad * sizeof(double), h->stream));
     GPX_CUDA(cudaMemcpyAsync(alpha, y, r.n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    const int bs = gpx_block_size_for(r.npad);
-    if (bs > GPX_T && r.npad >= 2 * bs) {
-        double* Dbig = r.solve_ws;
-        double* work = Dbig + (size_t)r.npad * bs;
-        double* tmp = work + (size_t)r.npad * bs / 4 + GPX_T;
-        GPX_TRY(gpx_block_inverses(h, r.Lfull, r.npad, r.npad, r.dinv, bs, Dbig, work));
-        GPX_TRY(gpx_trsv_big(h, r.Lfull, r.npad, r.npad, Dbig, bs, 0, alpha, tmp));
-        GPX_TRY(gpx_trsv_big(h, r.Lfull, r.npad, r.npad, Dbig, bs, 1, alpha, tmp));
+    SolveWs w = solve_ws_of(r);     // block inverses must have been built (build_block_inverses)
+    if (w.use) {
+        GPX_TRY(gpx_trsv_big(h, r.Lfull, r.npad, r.npad, w.Dbig, w.bs, 0, alpha, w.tmp));
+        GPX_TRY(gpx_trsv_big(h, r.Lfull, r.npad, r.npad, w.Dbig, w.bs, 1, alpha, w.tmp));
     } else {
         GPX_TRY(gpx_trsv(h, r.Lfull, r.npad, r.npad, r.dinv, 0, alpha));
         GPX_TRY(gpx_trsv(h, r.Lfull, r.npad, r.npad, r.dinv, 1, alpha));
@@ -312,6 +328,7 @@ int init_rank(MgRank& r, gpx_ctx* h, int P, int p, int64_t n, int nb, double* ws
     r.stage[1] = w; w += stage_elems(r.npad, nb);
     r.vec = w; w += 4 * (size_t)r.npad;
     r.solve_ws = w; w += solve_ws_elems(r.npad);
+    r.trsm_tmp = w; w += (size_t)gpx_block_size_for(r.npad) * r.wloc;
     return 0;
 }
 
@@ -433,7 +450,7 @@ extern "C" int64_t gpx_mg_workspace_elems(int64_t n, int nb, int world) {
     const int64_t npad = gpx_mg_padded_dim(n, nb, world);
     const int64_t wloc = npad / world;
     return 2 * npad * wloc + npad * npad + (npad / GPX_T) * GPX_T * GPX_T + 2 * (int64_t)stage_elems(npad, nb) + 4 * npad +
-           (int64_t)solve_ws_elems(npad);
+           (int64_t)solve_ws_elems(npad) + (int64_t)gpx_block_size_for(npad) * wloc;
 }
 
 // where the pieces live inside the workspace (element offsets): out6 = {Aloc, Xloc (local block columns of K^-1 after a
@@ -504,14 +521,11 @@ extern "C" int gpx_mg_potrs_vec(gpx_handle h, int64_t n, int nb, double* ws, dou
     GPX_ENTER(h);
     MgRank r;
     init_rank(r, h, h->world, h->rank, n, nb, ws);
-    const int bs = gpx_block_size_for(r.npad);
-    if (bs > GPX_T && r.npad >= 2 * bs) {
-        double* Dbig = r.solve_ws;
-        double* work = Dbig + (size_t)r.npad * bs;
-        double* tmp = work + (size_t)r.npad * bs / 4 + GPX_T;
-        GPX_TRY(gpx_block_inverses(h, r.Lfull, r.npad, r.npad, r.dinv, bs, Dbig, work));
-        GPX_TRY(gpx_trsv_big(h, r.Lfull, r.npad, r.npad, Dbig, bs, 0, x, tmp));
-        return gpx_trsv_big(h, r.Lfull, r.npad, r.npad, Dbig, bs, 1, x, tmp);
+    SolveWs w = solve_ws_of(r);
+    if (w.use) {
+        GPX_TRY(build_block_inverses(r));
+        GPX_TRY(gpx_trsv_big(h, r.Lfull, r.npad, r.npad, w.Dbig, w.bs, 0, x, w.tmp));
+        return gpx_trsv_big(h, r.Lfull, r.npad, r.npad, w.Dbig, w.bs, 1, x, w.tmp);
     }
     GPX_TRY(gpx_trsv(h, r.Lfull, r.npad, r.npad, r.dinv, 0, x));
     return gpx_trsv(h, r.Lfull, r.npad, r.npad, r.dinv, 1, x);
@@ -536,6 +550,7 @@ extern "C" int gpx_mg_fit_grad(gpx_handle h, int kind, const double* X, int64_t 
         return info;
     }
     cudaStream_t S = h->stream, H = h->aux2_stream;
+    GPX_TRY(build_block_inverses(r));
     if (!with_grad) {
         gpx_phase_mark(h, GPX_PH_SOLVE);
         GPX_TRY(solve_lml(r, y, alpha, out3));
@@ -647,9 +662,11 @@ extern "C" int gpx_mg_emulate_fit_grad(gpx_handle h, int P, int kind, const doub
     int info = 0;
     GPX_TRY(gpx_read_info(h, &info));
     if (info > 0) return info;
+    GPX_TRY(build_block_inverses(R[0]));
     GPX_TRY(solve_lml(R[0], y, alpha, out3));
     GPX_CUDA(cudaMemsetAsync(grad, 0, ntheta * sizeof(double), S));
     for (int p = 0; p < P; ++p) {
+        if (p > 0) GPX_TRY(build_block_inverses(R[p]));
         GPX_TRY(inverse_local(R[p]));
         GPX_TRY(grad_local(R[p], kind, X, D, theta_host, ntheta, alpha, grad, h->d_theta));  // sums over ranks = all-reduce
     }

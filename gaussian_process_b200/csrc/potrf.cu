@@ -769,7 +769,12 @@ namespace {
 // Left lower TRSM  L X = B  where only a *prefix* of B's columns is non-zero in any given row range: for rows
 // below global row r (relative to this sub-problem's row 0 at global row `grow0`), the non-zero columns are the
 // local blocks whose global block index is <= block(r): count = prefix(r).  Used for L^-1 on block-cyclic columns.
-struct PrefixMap { int P, p, nb, snake; };
+struct PrefixMap {
+    int P, p, nb, snake;
+    // optional explicit inverses of the bs x bs diagonal blocks of L (gpx_block_inverses) + a bs x ncols scratch: the
+    // recursion then stops at bs (one triangular GEMM per block instead of ~15 latency-bound launches per 1024 rows)
+    const double* D = nullptr; int bs = 0; double* tmp = nullptr;
+};
 inline int64_t prefix_cols(const PrefixMap& pm, int64_t grow_end) {
     // number of local columns (elements) whose global block start is < grow_end
     const int64_t nblk_below = (grow_end + pm.nb - 1) / pm.nb;              // global blocks 0..nblk_below-1 start below grow_end
@@ -779,6 +784,18 @@ int trsm_left_prefix(gpx_ctx* h, const double* L, int64_t n, int64_t ldl, const 
                      int64_t grow0, const PrefixMap& pm) {
     const int64_t ncols = prefix_cols(pm, grow0 + n);   // columns that can be non-zero within these rows
     if (ncols <= 0) return 0;
+    if (pm.D && n == pm.bs && grow0 % pm.bs == 0) {
+        GemmArgs a = base_args();   // tmp = D_b B (k <= row tile), copied back
+        a.A = pm.D + (grow0 / pm.bs) * (int64_t)pm.bs * pm.bs; a.lda = pm.bs; a.a_kmajor = 1;
+        a.B = B; a.ldb = ldb; a.b_kmajor = 0;
+        a.C = pm.tmp; a.ldc = ncols;
+        a.M = pm.bs; a.N = (int)ncols; a.K = pm.bs;
+        a.ke_mode = 1; a.rev_rows = 1;
+        GPX_TRY(gpx_gemm_launch(h, a));
+        GPX_CUDA(cudaMemcpy2DAsync(B, ldb * sizeof(double), pm.tmp, ncols * sizeof(double), ncols * sizeof(double), pm.bs,
+                                   cudaMemcpyDeviceToDevice, h->stream));
+        return 0;
+    }
     if (n == LT) {
         GemmArgs a = base_args();
         a.A = dinv; a.lda = LT; a.a_kmajor = 1;
@@ -807,8 +824,9 @@ int trsm_left_prefix(gpx_ctx* h, const double* L, int64_t n, int64_t ldl, const 
 }  // namespace
 
 int gpx_trsm_left_prefix_block(gpx_ctx* h, const double* L, int64_t n, int64_t ldl, const double* dinv, double* B, int64_t ldb,
-                               int P, int p, int nb, int snake) {
+                               int P, int p, int nb, int snake, const double* D, int bs, double* tmp) {
     PrefixMap pm{P, p, nb, snake};
+    if (D && tmp && bs > LT) { pm.D = D; pm.bs = bs; pm.tmp = tmp; }
     return trsm_left_prefix(h, L, n, ldl, dinv, B, ldb, 0, pm);
 }
 
@@ -822,6 +840,18 @@ int trsm_left_prefix_trans(gpx_ctx* h, const double* L, int64_t n, int64_t ldl, 
                            int64_t grow0, const PrefixMap& pm) {
     const int64_t ncols = prefix_cols(pm, grow0 + n);
     if (ncols <= 0) return 0;
+    if (pm.D && n == pm.bs && grow0 % pm.bs == 0) {
+        GemmArgs a = base_args();   // tmp = D_b^T X (k >= row tile), copied back
+        a.A = pm.D + (grow0 / pm.bs) * (int64_t)pm.bs * pm.bs; a.lda = pm.bs; a.a_kmajor = 0;
+        a.B = B; a.ldb = ldb; a.b_kmajor = 0;
+        a.C = pm.tmp; a.ldc = ncols;
+        a.M = pm.bs; a.N = (int)ncols; a.K = pm.bs;
+        a.kb_mode = 1;
+        GPX_TRY(gpx_gemm_launch(h, a));
+        GPX_CUDA(cudaMemcpy2DAsync(B, ldb * sizeof(double), pm.tmp, ncols * sizeof(double), ncols * sizeof(double), pm.bs,
+                                   cudaMemcpyDeviceToDevice, h->stream));
+        return 0;
+    }
     if (n == LT) {
         GemmArgs a = base_args();  // Z = Dinv^T X (in place; a CTA reads exactly the column range it writes)
         a.A = dinv; a.lda = LT; a.a_kmajor = 0;
@@ -849,8 +879,9 @@ int trsm_left_prefix_trans(gpx_ctx* h, const double* L, int64_t n, int64_t ldl, 
 }  // namespace
 
 int gpx_trsm_left_prefix_trans_block(gpx_ctx* h, const double* L, int64_t n, int64_t ldl, const double* dinv, double* B,
-                                     int64_t ldb, int P, int p, int nb, int snake) {
+                                     int64_t ldb, int P, int p, int nb, int snake, const double* D, int bs, double* tmp) {
     PrefixMap pm{P, p, nb, snake};
+    if (D && tmp && bs > LT) { pm.D = D; pm.bs = bs; pm.tmp = tmp; }
     return trsm_left_prefix_trans(h, L, n, ldl, dinv, B, ldb, 0, pm);
 }
 
