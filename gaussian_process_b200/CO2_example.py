@@ -217,6 +217,19 @@ def tune_hyperparameters_BO(X_train, X_test, y_train, num_iterations=10, n_hyper
     return hyperparms_train[max_index][0]
 
 
+def tune_hyperparameters_gradient(X_train, y_train, hyperparms, mask=None, step_size=1e-4, tolerance=1e-3, max_iter=100):
+    """Gradient ascent on the log marginal likelihood over the 11 hyper-parameters (or the subset with mask[j] != 0): the
+    gradient-based counterpart of tune_hyperparameters_BO (CO2...:330-379), same loop as tune...:121-153.  All state stays on
+    the device, one iteration is one CUDA-graph launch (gpx_gp_ascent).
+    Returns (theta, log marginal likelihood of the last iteration, iterations)."""
+    eng = get_engine()
+    th = _theta(hyperparms)
+    mk = np.ones(11, dtype=np.int32) if mask is None else np.asarray(mask, dtype=np.int32)
+    res = eng.ascend(COV_CO2, np.asarray(X_train, dtype=np.float64), y_train, th, mk, NOISE_VARIANCE, step_size, tolerance,
+                     max_iter)
+    return res["theta"], np.float64(res["lml"]), res["iterations"]
+
+
 def synthetic_mauna_loa(N=468, seed=0):
     """Mauna-Loa-shaped monthly series (the reference's fetch_mldata source is gone)."""
     t = 1958 + np.arange(N) / 12.0

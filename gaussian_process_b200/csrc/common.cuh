@@ -134,10 +134,10 @@ int gpx_gemm_tma_try_launch(gpx_ctx* h, const GemmArgs& a, double flops_exec);
 
 int gpx_lml_grad_block(gpx_ctx* h, int kind, const double* X, int64_t n, int D, const double* theta_host, int ntheta,
                        const double* Kinv, int64_t ldk, const double* alpha, double* grad, int64_t rows, int64_t cols, int rg0,
-                       int cg0);
+                       int cg0, const double* theta_dev = nullptr);
 int gpx_cov_build_block(gpx_ctx* h, int kind, const double* X, int64_t n, int D, const double* theta_host, int ntheta,
                         double diag_add, int flags, double* K, int64_t rows, int64_t cols, int64_t ldk, int rg0, int cg0,
-                        const double* scale = nullptr);
+                        const double* scale = nullptr, const double* theta_dev = nullptr);
 int gpx_potrf_block(gpx_ctx* h, double* A, int64_t n, int64_t lda, double* dinv, int goff);
 int gpx_trsm_right_lt_block(gpx_ctx* h, double* B, int64_t m, int64_t ldb, const double* L, int64_t n, int64_t ldl,
                             const double* dinv);

@@ -65,11 +65,19 @@ __device__ __forceinline__ void tile_accumulate(const CovParams& p, const double
 }
 
 template <int KIND, bool WITH_DK>
-__global__ void __launch_bounds__(CTHREADS) cov_build_kernel(CovParams p, const double* __restrict__ X1, int64_t n1,
+__global__ void __launch_bounds__(CTHREADS) cov_build_kernel(CovParams p_in, const double* __restrict__ X1, int64_t n1,
                                                             const double* __restrict__ X2, int64_t n2, double diag_add,
                                                             int flags, double* __restrict__ K, int64_t ldk,
                                                             double* __restrict__ dK, int64_t dk_stride, int rg0, int cg0,
-                                                            const double* __restrict__ scale) {
+                                                            const double* __restrict__ scale,
+                                                            const double* __restrict__ theta_dev) {
+    // theta_dev (optional): the hyper-parameters are read from DEVICE memory instead of the launch parameters, so that a
+    // captured CUDA graph of an optimiser iteration sees the values the previous iteration wrote (ascent.cu).
+    CovParams p = p_in;
+    if (theta_dev) {
+#pragma unroll
+        for (int q = 0; q < NTheta<KIND>::value; ++q) p.th[q] = theta_dev[q];
+    }
     // scale (optional, square blocks): K[i,j] <- scale[i] k_ij scale[j] before the diagonal term is added, so that
     // B = I + W^1/2 K W^1/2 (GP_binary_classification.py:107) is built straight from X with diag_add = 1.
     // rg0 / cg0: global row / column index of this launch's element (0,0) -- K points at that element; used by
@@ -132,10 +140,15 @@ __global__ void __launch_bounds__(CTHREADS) cov_build_kernel(CovParams p, const 
 
 // grad partials: partial[block][q] = sum over this lower tile of w_ij * dK_ij,q
 template <int KIND>
-__global__ void __launch_bounds__(CTHREADS) lml_grad_kernel(CovParams p, const double* __restrict__ X, int64_t n,
+__global__ void __launch_bounds__(CTHREADS) lml_grad_kernel(CovParams p_in, const double* __restrict__ X, int64_t n,
                                                            const double* __restrict__ Kinv, int64_t ldk,
                                                            const double* __restrict__ alpha, double* __restrict__ partial,
-                                                           int rg0, int cg0) {
+                                                           int rg0, int cg0, const double* __restrict__ theta_dev) {
+    CovParams p = p_in;
+    if (theta_dev) {
+#pragma unroll
+        for (int q = 0; q < NTheta<KIND>::value; ++q) p.th[q] = theta_dev[q];
+    }
     __shared__ double xs1[TM * DCH];
     __shared__ double xs2[DCH * TN];
     __shared__ double red[CTHREADS / 32][11];
@@ -227,20 +240,20 @@ int make_params(int kind, int D, const double* theta, int ntheta, CovParams* p) 
 template <bool WITH_DK>
 int launch_build(gpx_ctx* h, const CovParams& p, const double* X1, int64_t n1, const double* X2, int64_t n2, double diag_add,
                  int flags, double* K, int64_t n1p, int64_t n2p, int64_t ldk, double* dK, int64_t dk_stride, int rg0 = 0,
-                 int cg0 = 0, const double* scale = nullptr) {
+                 int cg0 = 0, const double* scale = nullptr, const double* theta_dev = nullptr) {
     dim3 grid((unsigned)(n2p / TN), (unsigned)(n1p / TM));
     switch (p.kind) {
         case GPX_COV_SE:
-            cov_build_kernel<GPX_COV_SE, WITH_DK><<<grid, CTHREADS, 0, h->stream>>>(p, X1, n1, X2, n2, diag_add, flags, K, ldk, dK, dk_stride, rg0, cg0, scale);
+            cov_build_kernel<GPX_COV_SE, WITH_DK><<<grid, CTHREADS, 0, h->stream>>>(p, X1, n1, X2, n2, diag_add, flags, K, ldk, dK, dk_stride, rg0, cg0, scale, theta_dev);
             break;
         case GPX_COV_LIN:
-            cov_build_kernel<GPX_COV_LIN, WITH_DK><<<grid, CTHREADS, 0, h->stream>>>(p, X1, n1, X2, n2, diag_add, flags, K, ldk, dK, dk_stride, rg0, cg0, scale);
+            cov_build_kernel<GPX_COV_LIN, WITH_DK><<<grid, CTHREADS, 0, h->stream>>>(p, X1, n1, X2, n2, diag_add, flags, K, ldk, dK, dk_stride, rg0, cg0, scale, theta_dev);
             break;
         case GPX_COV_PER:
-            cov_build_kernel<GPX_COV_PER, WITH_DK><<<grid, CTHREADS, 0, h->stream>>>(p, X1, n1, X2, n2, diag_add, flags, K, ldk, dK, dk_stride, rg0, cg0, scale);
+            cov_build_kernel<GPX_COV_PER, WITH_DK><<<grid, CTHREADS, 0, h->stream>>>(p, X1, n1, X2, n2, diag_add, flags, K, ldk, dK, dk_stride, rg0, cg0, scale, theta_dev);
             break;
         default:
-            cov_build_kernel<GPX_COV_CO2, WITH_DK><<<grid, CTHREADS, 0, h->stream>>>(p, X1, n1, X2, n2, diag_add, flags, K, ldk, dK, dk_stride, rg0, cg0, scale);
+            cov_build_kernel<GPX_COV_CO2, WITH_DK><<<grid, CTHREADS, 0, h->stream>>>(p, X1, n1, X2, n2, diag_add, flags, K, ldk, dK, dk_stride, rg0, cg0, scale, theta_dev);
             break;
     }
     GPX_CHECK_LAUNCH(h);
@@ -308,7 +321,7 @@ extern "C" int gpx_cov_build(gpx_handle h, int kind, const double* X1, int64_t n
 // `rows` x `cols` elements (multiples of 128); grad (device, ntheta doubles) receives this block's contribution.
 int gpx_lml_grad_block(gpx_ctx* h, int kind, const double* X, int64_t n, int D, const double* theta_host, int ntheta,
                        const double* Kinv, int64_t ldk, const double* alpha, double* grad, int64_t rows, int64_t cols, int rg0,
-                       int cg0) {
+                       int cg0, const double* theta_dev) {
     GPX_REQUIRE(kind >= 0 && kind <= 3, 2);
     CovParams p;
     GPX_TRY(make_params(kind, D, theta_host, ntheta, &p));
@@ -326,10 +339,10 @@ int gpx_lml_grad_block(gpx_ctx* h, int kind, const double* X, int64_t n, int D, 
     }
     dim3 grid(ntc, ntr);
     switch (kind) {
-        case GPX_COV_SE: lml_grad_kernel<GPX_COV_SE><<<grid, CTHREADS, 0, h->stream>>>(p, X, n, Kinv, ldk, alpha, h->d_partial, rg0, cg0); break;
-        case GPX_COV_LIN: lml_grad_kernel<GPX_COV_LIN><<<grid, CTHREADS, 0, h->stream>>>(p, X, n, Kinv, ldk, alpha, h->d_partial, rg0, cg0); break;
-        case GPX_COV_PER: lml_grad_kernel<GPX_COV_PER><<<grid, CTHREADS, 0, h->stream>>>(p, X, n, Kinv, ldk, alpha, h->d_partial, rg0, cg0); break;
-        default: lml_grad_kernel<GPX_COV_CO2><<<grid, CTHREADS, 0, h->stream>>>(p, X, n, Kinv, ldk, alpha, h->d_partial, rg0, cg0); break;
+        case GPX_COV_SE: lml_grad_kernel<GPX_COV_SE><<<grid, CTHREADS, 0, h->stream>>>(p, X, n, Kinv, ldk, alpha, h->d_partial, rg0, cg0, theta_dev); break;
+        case GPX_COV_LIN: lml_grad_kernel<GPX_COV_LIN><<<grid, CTHREADS, 0, h->stream>>>(p, X, n, Kinv, ldk, alpha, h->d_partial, rg0, cg0, theta_dev); break;
+        case GPX_COV_PER: lml_grad_kernel<GPX_COV_PER><<<grid, CTHREADS, 0, h->stream>>>(p, X, n, Kinv, ldk, alpha, h->d_partial, rg0, cg0, theta_dev); break;
+        default: lml_grad_kernel<GPX_COV_CO2><<<grid, CTHREADS, 0, h->stream>>>(p, X, n, Kinv, ldk, alpha, h->d_partial, rg0, cg0, theta_dev); break;
     }
     GPX_CHECK_LAUNCH(h);
     grad_finish_kernel<<<ntheta, 256, 0, h->stream>>>(ntr * ntc, ntheta, h->d_partial, grad);
@@ -340,15 +353,15 @@ int gpx_lml_grad_block(gpx_ctx* h, int kind, const double* X, int64_t n, int D, 
 // Covariance block whose element (0,0) has global index (rg0, cg0): rows x cols elements written at K (ld ldk).
 int gpx_cov_build_block(gpx_ctx* h, int kind, const double* X, int64_t n, int D, const double* theta_host, int ntheta,
                         double diag_add, int flags, double* K, int64_t rows, int64_t cols, int64_t ldk, int rg0, int cg0,
-                        const double* scale) {
+                        const double* scale, const double* theta_dev) {
     CovParams p;
     GPX_TRY(make_params(kind, D, theta_host, ntheta, &p));
-    return launch_build<false>(h, p, X, n, X, n, diag_add, flags, K, rows, cols, ldk, nullptr, 0, rg0, cg0, scale);
+    return launch_build<false>(h, p, X, n, X, n, diag_add, flags, K, rows, cols, ldk, nullptr, 0, rg0, cg0, scale, theta_dev);
 }
 
 extern "C" int gpx_lml_grad(gpx_handle h, int kind, const double* X, int64_t n, int D, const double* theta_host, int ntheta,
                             const double* Kinv, int64_t ldk, const double* alpha, double* grad) {
     GPX_ENTER(h);
     const int64_t np_ = ((n + TM - 1) / TM) * TM;
-    return gpx_lml_grad_block(h, kind, X, n, D, theta_host, ntheta, Kinv, ldk, alpha, grad, np_, np_, 0, 0);
+    return gpx_lml_grad_block(h, kind, X, n, D, theta_host, ntheta, Kinv, ldk, alpha, grad, np_, np_, 0, 0, nullptr);
 }

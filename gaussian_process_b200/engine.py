@@ -283,6 +283,32 @@ class Engine:
         return GPFit(kind, th, float(s), n, npad, Xd, yd, A, dinv, alpha, float(o[0]), float(o[1]), float(o[2]),
                      grad=o[3:3 + len(th)].copy() if with_grad else None, Kinv=Kinv, L_is_inverse=with_grad)
 
+    def ascend(self, kind: int, X, y, theta0, mask, s: float, step: float, tol: float, max_iter: int, use_graph: bool = True,
+               ws=None):
+        """Device-resident gradient ascent on the LML over the masked hyper-parameters (gpx_gp_ascent; tune...:121-153
+        generalised).  Returns dict(theta, theta_used, iterations, lml, error, converged, history)."""
+        self._sync_stream()
+        Xd = self.to_device(X)
+        yd = self.to_device(np.asarray(y).reshape(-1) if not hasattr(y, "data_ptr") else y.reshape(-1))
+        n, D = Xd.shape
+        th = np.ascontiguousarray(np.asarray(theta0, dtype=np.float64).reshape(-1)).copy()
+        mk = np.ascontiguousarray(np.asarray(mask, dtype=np.int32).reshape(-1))
+        if mk.size != th.size:
+            raise ValueError("mask must have one entry per hyper-parameter")
+        if ws is None:
+            ws = self.empty(int(self.lib.gpx_gp_ascent_ws_elems(n)))
+        used = np.empty_like(th)
+        out4 = np.zeros(4)
+        hist = np.zeros(int(max_iter))
+        st = self.lib.gpx_gp_ascent(self.h, kind, self._p(Xd), n, D, ctypes.c_void_p(th.ctypes.data), th.size,
+                                    ctypes.c_void_p(mk.ctypes.data), float(s), self._p(yd), float(step), float(tol), int(max_iter),
+                                    int(bool(use_graph)), self._p(ws), ctypes.c_void_p(used.ctypes.data),
+                                    ctypes.c_void_p(out4.ctypes.data), ctypes.c_void_p(hist.ctypes.data))
+        check(st, "gpx_gp_ascent")
+        it = int(out4[0])
+        return dict(theta=th, theta_used=used, iterations=it, lml=float(out4[1]), error=float(out4[2]), converged=bool(out4[3]),
+                    history=hist[:it].copy())
+
     def lml_grad(self, kind: int, Xd, theta, Kinv, alpha, n=None) -> np.ndarray:
         """.5 sum_ik (alpha_i alpha_k - Kinv_ik) dK_ik/dtheta_j for every theta_j (fused kernel) -> host array."""
         self._sync_stream()

@@ -91,37 +91,39 @@ def tune_hyperparms_first(X_train, X_test, y_train, num_fun, sigma, l):
     yd = eng.to_device(np.asarray(y_train, dtype=np.float64).reshape(-1))
     Xs = eng.to_device(X_test)
     N = Xs.shape[0]
-    log_marg_likelihood_old = 0
     sig = float(np.asarray(sigma).reshape(-1)[0])
-    pred = None
-    for i in range(10000):
-        lcur = float(np.asarray(l).reshape(-1)[0])
-        theta = [sig, lcur]
-        fit = eng.fit(COV_SE, Xd, yd, theta, NOISE_VARIANCE)               # tune...:123-129,141
-        log_marg_likelihood = np.float64(fit.lml)
-        error = np.sqrt(np.sum((log_marg_likelihood - log_marg_likelihood_old) ** 2))
-        last = error <= TOLERANCE or i == 9999
-        if last:                                                            # tune...:132-137 for the iteration kept
-            mu, var, V = eng.predict(fit, Xs, want_v=True)
-            pred = (eng.to_host(mu), eng.to_host(var), V, theta)
-        # tune...:144-145: K_y^-1 then one ascent step (always taken before the convergence test)
-        Kinv = eng.inverse_from_factor(fit)
-        l = l + STEP_SIZE * eng.lml_grad(COV_SE, Xd, theta, Kinv, fit.alpha, n=fit.n)[1]
-        log_marg_likelihood_old = log_marg_likelihood
-        if error <= TOLERANCE:
-            print("The hyperparameter tuning function has already converged after " + repr(i + 1) + " iterations!")
-            print("The error is " + _r(error))
-            print("training end!")
-            break
-    optimal_likelihood = log_marg_likelihood
+    l0 = float(np.asarray(l).reshape(-1)[0])
+    # tune...:121-153 as ONE libgpx call: theta, LML history and the convergence test stay on the device, one iteration
+    # (K build, Cholesky, solves, LML, K^-1, fused gradient, step on l) is one CUDA-graph launch.  Only l moves (the
+    # reference's sigma update is commented out, :46-62).
+    res = eng.ascend(COV_SE, Xd, yd, [sig, l0], [0, 1], NOISE_VARIANCE, STEP_SIZE, TOLERANCE, 10000)
+    l = np.full(np.shape(l), res["theta"][1]) if isinstance(l, np.ndarray) else res["theta"][1]
+    if res["converged"]:
+        print("The hyperparameter tuning function has already converged after " + repr(res["iterations"]) + " iterations!")
+        print("The error is " + _r(res["error"]))
+        print("training end!")
+    optimal_likelihood = np.float64(res["lml"])
     print('optimal lenghscalar is: ' + _r(l))
     print('maximum log marginal likelihood is: ' + _r(optimal_likelihood))
-    mu_post, var, V, theta = pred
+    theta = [sig, float(res["theta_used"][1])]
+    fit = eng.fit(COV_SE, Xd, yd, theta, NOISE_VARIANCE)                    # tune...:132-137 at the theta of the last iteration
+    mu, var, V = eng.predict(fit, Xs, want_v=True)
+    mu_post, var = eng.to_host(mu), eng.to_host(var)
     with np.errstate(invalid="ignore"):
         stand_devi = np.sqrt(var)
     L_, _ = eng.posterior_sample_factor(COV_SE, theta, Xs, V, 1e-6)         # tune...:159
     f_post_fun = mu_post.reshape(-1, 1) + eng.tri_times(L_, np.random.normal(size=(N, num_fun)), N)
     return mu_post, stand_devi, f_post_fun, optimal_likelihood
+
+
+def tune_hyperparms_all(X_train, y_train, sigma, l, step_size=STEP_SIZE, tolerance=TOLERANCE, max_iter=10000):
+    """Gradient ascent on BOTH sigma and l (the update the reference leaves commented out, tune...:46-62, switched on):
+    returns (sigma, l, log marginal likelihood, iterations).  Device-resident loop (gpx_gp_ascent)."""
+    eng = get_engine()
+    res = eng.ascend(COV_SE, np.asarray(X_train, dtype=np.float64), y_train,
+                     [float(np.asarray(sigma).reshape(-1)[0]), float(np.asarray(l).reshape(-1)[0])], [1, 1], NOISE_VARIANCE,
+                     step_size, tolerance, max_iter)
+    return res["theta"][0], res["theta"][1], np.float64(res["lml"]), res["iterations"]
 
 
 def _tune_first_small(eng, X_train, X_test, y_train, num_fun, sigma, l):

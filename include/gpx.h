@@ -155,6 +155,21 @@ int gpx_gp_fit_grad(gpx_handle h, int kind, const double* X, int64_t n, int D, c
                     double s, const double* y, double* A, int64_t np_, int64_t lda, double* dinv,
                     double* Kinv, double* alpha, double* out3, double* grad);
 
+/* ---- N1: device-resident hyper-parameter optimiser -------------------------------------------------------------
+ * Gradient ascent on the log marginal likelihood over the hyper-parameters j with mask[j] != 0: per iteration
+ * K(theta) + sI -> Cholesky -> alpha -> LML -> K^-1 -> dLML/dtheta -> theta_j += step * grad_j, until
+ * |LML - LML_prev| <= tol (LML_prev starts at 0; the step of the converging iteration is still taken) or max_iter.
+ * Replaces the loop of tune_hyperparms_regression.py:121-153 (mask = {0, 1}: only l moves, as shipped) and extends it to
+ * sigma and to the 11 hyper-parameters of CO2_example.py.  theta, history and convergence state live on the device;
+ * with use_graph != 0 one iteration is ONE CUDA-graph launch (captured on the second iteration) + a 40-byte read-back.
+ * X, y: device; ws: gpx_gp_ascent_ws_elems(n) doubles (device); theta_io / mask / theta_used_out / out4 / history: HOST.
+ * out4 = {iterations, LML of the last iteration, its |LML - LML_prev|, converged}; theta_io returns theta after the last
+ * step, theta_used_out the theta the last iteration was evaluated at.  Returns > 0 if a K(theta) is not positive definite. */
+int64_t gpx_gp_ascent_ws_elems(int64_t n);
+int gpx_gp_ascent(gpx_handle h, int kind, const double* X, int64_t n, int D, double* theta_io, int ntheta, const int* mask,
+                  double s, const double* y, double step, double tol, int max_iter, int use_graph, double* ws,
+                  double* theta_used_out, double* out4, double* history);
+
 /* ---- A10/A11: Laplace building blocks --------------------------------------------------------*/
 /* binary (GP_binary_classification.py:48-83,104-105): mode 0 = reference-faithful gradient
  * t - sigmoid(y f), mode 1 = textbook t - sigmoid(f); w = sigmoid(f)(1-sigmoid(f)); sw = sqrt(w). */

@@ -193,3 +193,76 @@ def test_script_main_blocks_run_end_to_end(module, needle):
     assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
     if needle:
         assert needle in out.stdout
+
+
+# ------------------------------------------------------------------------------------------------ N1 optimiser drivers
+def _numpy_ascent(lml_grad_fn, theta0, mask, step, tol, max_iter):
+    """The loop of tune_hyperparms_regression.py:121-153 around any (LML, gradient) oracle."""
+    th = np.array(theta0, dtype=np.float64)
+    prev, hist = 0.0, []
+    used = th.copy()
+    for it in range(max_iter):
+        lml, g = lml_grad_fn(th)
+        used = th.copy()
+        th = th + step * np.where(mask, g, 0.0)
+        err = abs(lml - prev)
+        prev = lml
+        hist.append(lml)
+        if err <= tol:
+            break
+    return th, used, np.array(hist)
+
+
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_ascent_sigma_and_l_matches_numpy_loop(eng, use_graph):
+    """gpx_gp_ascent over BOTH SE hyper-parameters (CUDA-graph replay and eager) vs the same loop on the oracle."""
+    from gaussian_process_b200._lib import COV_SE
+    X, y = O.synth_c5(300, 3)
+
+    def f(th):
+        K = O.rbf_kernel(X, X, th[0], th[1]) + O.S_NOISE * np.eye(300)
+        Kinv = np.linalg.inv(K)
+        a = Kinv @ y
+        lml = -.5 * y @ a - .5 * np.linalg.slogdet(K)[1] - 150 * np.log(2 * np.pi)
+        return lml, O.lml_grad_from(a, Kinv, O.rbf_dcov(X, th[0], th[1]))
+
+    th_o, used_o, hist_o = _numpy_ascent(f, [1.0, 1.5], np.array([1, 1]), 1e-4, 1e-3, 12)
+    res = eng.ascend(COV_SE, X, y, [1.0, 1.5], [1, 1], O.S_NOISE, 1e-4, 1e-3, 12, use_graph=use_graph)
+    assert res["iterations"] == len(hist_o)
+    assert rel(res["history"], hist_o) < 1e-8
+    assert rel(res["theta"], th_o) < 1e-7 and rel(res["theta_used"], used_o) < 1e-7
+
+
+def test_ascent_co2_eleven_theta_matches_oracle_gradient_loop(eng):
+    """All 11 CO2 hyper-parameters ascended on the device (CO2_example.tune_hyperparameters_gradient) vs the oracle."""
+    from gaussian_process_b200 import CO2_example as C2
+    X, y, _ = O.synth_c2(200)
+    th0 = O.CO2_THETA_BOOK * 1.05
+
+    def f(th):
+        K = O.co2_covariance(X, X, th) + O.S_NOISE * np.eye(200)
+        Kinv = np.linalg.inv(K)
+        a = Kinv @ y
+        return O.co2_lml(X, y, th), O.lml_grad_from(a, Kinv, O.co2_dcov(X, th))
+
+    mask = np.array([1, 0, 1, 0, 1, 1, 1, 1, 1, 1, 1])
+    th_o, used_o, hist_o = _numpy_ascent(f, th0, mask, 1e-6, 1e-9, 4)
+    th, lml, it = C2.tune_hyperparameters_gradient(X, y, th0, mask=mask, step_size=1e-6, tolerance=1e-9, max_iter=4)
+    assert it == 4 and abs(lml - hist_o[-1]) <= 1e-8 * abs(hist_o[-1])
+    assert np.all(np.abs(th - th_o) <= 1e-6 * np.maximum(1.0, np.abs(th_o)))
+    assert th[1] == th0[1] and th[3] == th0[3]          # masked hyper-parameters do not move
+
+
+def test_tune_first_tiled_path_is_one_device_loop(eng):
+    """tune_hyperparms_first above the fused small-problem size: same iterations / LML / moments as the oracle loop."""
+    from gaussian_process_b200 import tune_hyperparms_regression as T
+    X, y, Xs = O.synth_c1(200, 150)
+    np.random.seed(2)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        mu, sd, fp, lml = T.tune_hyperparms_first(X, Xs, y, 2, 1.0, np.array([0.8]))
+    np.random.seed(2)
+    mu_o, sd_o, fp_o, lml_o, l_o, it_o = O.tune_first(X, Xs, y, 2, 1.0, np.array([0.8]))
+    assert ("after %d iterations" % it_o) in buf.getvalue()
+    assert abs(lml - lml_o) <= 1e-8 * abs(lml_o)
+    assert rel(mu, mu_o) < 1e-7 and rel(sd ** 2, sd_o ** 2) < 1e-6
