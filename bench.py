@@ -429,44 +429,65 @@ def make_c3(args, eng, n, D, world, rank, torch):
     from gaussian_process_b200.laplace import BinaryLaplace
     w = Workload()
     X, y, fpr = S.synth_c3(n, D)
-    Xd = eng.to_device(X)
-    Kd = eng.cov(COV_SE, Xd, Xd, [1.0, 1.0], same_x=True)
-    model = BinaryLaplace(eng, Kd, n)
-    yd = model._pad_vec(y)
-    st = {"f": eng.zeros(model.npad), "fn": eng.zeros(model.npad), "it": 0}
-    model._workspace()
+    distributed = world > 1 or args.mg
+    if distributed:
+        # B = I + W^1/2 K W^1/2 factored by the block-cyclic multi-GPU Cholesky (gpx_mg_laplace_binary_step)
+        from gaussian_process_b200.distributed import BinaryLaplaceDistributed
+        model = BinaryLaplaceDistributed(eng, X, 1.0, 1.0, nb=args.nb)
+        npad_m = model.npad
+        yd = eng.zeros(npad_m)
+        yd[:n] = eng.to_device(y.reshape(-1))
+        st = {"f": eng.zeros(npad_m), "fn": eng.zeros(npad_m), "it": 0}
+        err_t = model.err
 
-    def step():   # one Newton iteration from the current iterate (the first steps are the real Newton trajectory from f = 0)
-        eng._sync_stream()
-        model.newton_step(yd, st["f"], st["fn"])
-        st["f"], st["fn"] = st["fn"], st["f"]
-        st["it"] += 1
+        def step():
+            eng._sync_stream()
+            model.step(yd, st["f"], st["fn"])
+            st["f"], st["fn"] = st["fn"], st["f"]
+            st["it"] += 1
+        w.host_step = None
+    else:
+        Xd = eng.to_device(X)
+        Kd = eng.cov(COV_SE, Xd, Xd, [1.0, 1.0], same_x=True)
+        model = BinaryLaplace(eng, Kd, n)
+        yd = model._pad_vec(y)
+        st = {"f": eng.zeros(model.npad), "fn": eng.zeros(model.npad), "it": 0}
+        model._workspace()
+        err_t = model._err
+
+        def step():   # one Newton iteration from the current iterate (the first steps are the real Newton trajectory from f = 0)
+            eng._sync_stream()
+            model.newton_step(yd, st["f"], st["fn"])
+            st["f"], st["fn"] = st["fn"], st["f"]
+            st["it"] += 1
+        Kh = {}
+
+        def host_step():   # public API: host K, y in; (W, L_inv, gradient) out -- whole fit, reported per Newton iteration
+            if "K" not in Kh:
+                Kh["K"] = eng.to_host(Kd[:n, :n])
+            t0 = time.perf_counter()
+            Wm, Linv, g = quiet(B.model_training, Kh["K"], y, fpr, 1, mode="newton")
+            st["e2e_iters"] = len(B._last_model["model"].errors)
+            st["e2e_total"] = time.perf_counter() - t0
+        w.host_step = host_step
     w.step = step
-    Kh = {}
-
-    def host_step():   # public API: host K, y in; (W, L_inv, gradient) out -- whole fit, reported per Newton iteration
-        if "K" not in Kh:
-            Kh["K"] = eng.to_host(Kd[:n, :n])
-        t0 = time.perf_counter()
-        Wm, Linv, g = quiet(B.model_training, Kh["K"], y, fpr, 1, mode="newton")
-        st["e2e_iters"] = len(B._last_model["model"].errors)
-        st["e2e_total"] = time.perf_counter() - t0
-    w.host_step = host_step
     w.e2e_per_iteration = True
     w.release = lambda: None
     npad = float(padded(n))
     w.h2d, w.d2h = int((n * n + 2 * n) * 8), int((n * n + 2 * n) * 8)
     w.alg_flops = npad ** 3 / 3
     w.flops_note = "one Cholesky of B = I + W^1/2 K W^1/2 (N^3/3) per Newton iteration"
-    w.parallelism = "single GPU" if world == 1 else "%d ranks" % world
+    w.parallelism = ("single GPU" if not distributed else
+                     "B built and factored block-cyclically (nb=%d) over %d GPU(s), NCCL panel broadcast; mat-vecs and solves "
+                     "replicated" % (args.nb, world))
     w.l2 = "K and B (%.1f GB each) larger than L2; no flush needed" % (npad * npad * 8 / 1e9)
     w.timing_handles = (eng,)
     w.exclusive_kernel_time = False
 
     def finish():
-        return {"newton_iterations_run": st["it"], "last_error": float(model._err[0].item()),
-                "e2e_note": "whole model_training(mode='newton') call incl. 2.1 GB H2D of K and D2H of inv(L): %.3f s for %d iterations"
-                            % (st.get("e2e_total", float("nan")), st.get("e2e_iters", 0))}
+        return {"newton_iterations_run": st["it"], "last_error": float(err_t[0].item()),
+                "e2e_note": ("whole model_training(mode='newton') call incl. 2.1 GB H2D of K and D2H of inv(L): %.3f s for %d iterations"
+                             % (st.get("e2e_total", float("nan")), st.get("e2e_iters", 0))) if not distributed else None}
     w.finish = finish
     w.state = st
     return w
@@ -607,7 +628,7 @@ def run_gpx(args, n, D):
             w.step()
     e1.record()
     barrier()
-    if cfg in ("c1", "c2"):   # short timed regions: keep the sampler alive long enough for a few samples under load
+    if cfg != "c5":           # short timed regions: keep the sampler alive long enough for a few samples under load
         t_end = time.time() + 1.0
         while time.time() < t_end:
             w.step()

@@ -73,6 +73,7 @@ extern "C" int gpx_destroy(gpx_handle h) {
     if (h->d_theta) cudaFree(h->d_theta);
     if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
     if (h->aux2_stream) cudaStreamDestroy(h->aux2_stream);
+    if (h->graph_stream) cudaStreamDestroy(h->graph_stream);
     if (h->ev_a) cudaEventDestroy(h->ev_a);
     if (h->ev_b) cudaEventDestroy(h->ev_b);
     delete h;

@@ -105,7 +105,14 @@ extern "C" int gpx_gp_ascent(gpx_handle h, int kind, const double* X, int64_t n,
     GPX_REQUIRE(max_iter >= 1, 13);
     const int64_t np_ = gpx_padded_dim(n);
     AscentWs w = carve(ws, np_);
-    cudaStream_t S = h->stream;
+    // The loop runs on a private stream: the caller's stream may be the legacy default stream, which cannot be captured.
+    cudaStream_t caller = h->stream;
+    if (!h->graph_stream) GPX_CUDA(cudaStreamCreateWithFlags(&h->graph_stream, cudaStreamNonBlocking));
+    cudaStream_t S = h->graph_stream;
+    GPX_CUDA(cudaEventRecord(h->ev_a, caller));           // X, y were produced on the caller's stream
+    GPX_CUDA(cudaStreamWaitEvent(S, h->ev_a, 0));
+    struct Restore { gpx_ctx* h; cudaStream_t s; ~Restore() { h->stream = s; } } restore{h, caller};
+    h->stream = S;
     AscentState init;
     memset(&init, 0, sizeof(init));
     for (int j = 0; j < ntheta; ++j) init.theta[j] = init.theta_used[j] = theta_io[j];
@@ -130,7 +137,13 @@ extern "C" int gpx_gp_ascent(gpx_handle h, int kind, const double* X, int64_t n,
         } else {
             if (!exec) {
                 h->timing_on = 0;                                                                     // no event pairs inside a capture
-                if (cudaStreamBeginCapture(S, cudaStreamCaptureModeRelaxed) != cudaSuccess) { rc = GPX_E_CUDA; break; }
+                cudaError_t eb = cudaStreamBeginCapture(S, cudaStreamCaptureModeRelaxed);
+                if (eb != cudaSuccess) {
+                    gpx_set_error("gpx_gp_ascent: cudaStreamBeginCapture failed: %s", cudaGetErrorString(eb));
+                    h->timing_on = timing_was;
+                    rc = GPX_E_CUDA;
+                    break;
+                }
                 rc = enqueue_iteration(h, kind, X, n, D, theta_io, ntheta, s, y, np_, w, step);
                 cudaError_t e = cudaStreamEndCapture(S, &graph);
                 h->timing_on = timing_was;

@@ -24,6 +24,7 @@ struct gpx_ctx {
     // NCCL (optional, dlopen'ed)
     void* nccl_comm; int rank, world;
     cudaStream_t aux_stream, aux2_stream; cudaEvent_t ev_a, ev_b;
+    cudaStream_t graph_stream;          // private capturable stream of the optimiser loop (ascent.cu), created on demand
     // optional instrumentation (timing.cu)
     int timing_on; void* timing;
 };
