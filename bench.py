@@ -10,6 +10,8 @@ N=65536, D=16, float64, synthetic data.  The other configs are se
     c2  CO2 composite kernel N=8192: compute_mar_likelihood + make_prediction(240)     step = both calls
     c3  binary Laplace N=16384 D=8, textbook Newton on B = I + W^1/2 K W^1/2           step = one Newton iteration
     c4  multiclass softmax Laplace C=10, n=8192, D=16 (classes sharded over ranks)     step = one Alg-3.3 iteration
+    c2p CO2 N=8192: posterior mean / variance of 2048 test points from the factor of the distributed fit, test points
+        sharded over the ranks                                             step = one prediction of all points
 
 Every line: `value` = seconds per step with the inputs resident in HBM (CUDA events on the launching stream, max over
 ranks); `e2e` = the same work through the public host-buffer API (H2D of the inputs and D2H of the results inside the
@@ -50,6 +52,7 @@ METRICS = {
     "c3": "binary_laplace_seconds_per_newton_iteration_n16384_fp64",
     "c2": "co2_lml_plus_prediction_seconds_n8192_fp64",
     "c1": "gp_regression_prediction_seconds_n5_fp64",
+    "c2p": "co2_prediction_2048_test_points_seconds_n8192_fp64",
 }
 
 
@@ -72,8 +75,8 @@ def parse():
     return ap.parse_args()
 
 
-DEFAULT_N = {"c5": (65536, 16), "c4": (8192, 16), "c3": (16384, 8), "c2": (8192, 1), "c1": (5, 1)}
-DEFAULT_CPU_N = {"c5": 4096, "c4": 512, "c3": 2048, "c2": 2048, "c1": 5}
+DEFAULT_N = {"c5": (65536, 16), "c4": (8192, 16), "c3": (16384, 8), "c2": (8192, 1), "c1": (5, 1), "c2p": (8192, 1)}
+DEFAULT_CPU_N = {"c5": 4096, "c4": 512, "c3": 2048, "c2": 2048, "c1": 5, "c2p": 2048}
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -191,6 +194,21 @@ def cpu_sample(config: str, n_full: int, d: int, n_sample: int):
         r = (n_full / n_sample) ** 3
         return t * r, t, ("oracle Alg-3.3 (GP_multi_classification.py:66-126 per iteration) at C=10 n=%d: %.2f s per iteration "
                           "over %d iterations; scaled by (%d/%d)^3" % (n_sample, t, it, n_full, n_sample))
+    if config == "c2p":
+        X, y, _ = S.synth_c2(n_sample, 240)
+        Xs = X[-1, 0] + (1 + np.arange(2048))[:, None] / 12.0
+        K = O.co2_covariance(X, X, O.CO2_THETA_BOOK) + O.S_NOISE * np.eye(n_sample)
+        L = np.linalg.cholesky(K)
+        alpha = np.linalg.solve(L.T, np.linalg.solve(L, y))
+        t0 = time.perf_counter()                       # CO2_example.py:196-208 given the factor
+        Ks = O.co2_covariance(X, Xs, O.CO2_THETA_BOOK)
+        mu = Ks.T @ alpha
+        v = np.linalg.solve(L, Ks)
+        var = np.diag(O.co2_covariance(Xs, Xs, O.CO2_THETA_BOOK)) - np.sum(v ** 2, axis=0)
+        t = time.perf_counter() - t0
+        r = (n_full / n_sample) ** 3                   # np.linalg.solve(L, K_s) LU-factors L: the N^3 term dominates
+        return t * r, t, ("oracle port of CO2_example.py:196-208 (K_s, mean, LU solve(L, K_s), variance) for 2048 test points at "
+                          "N=%d: %.2f s; scaled by (%d/%d)^3 (the reference's LU solve dominates)" % (n_sample, t, n_full, n_sample))
     X, y, Xs = S.synth_c1(n_full, 100)
     reps = 200
     np.random.seed(0)
@@ -225,6 +243,7 @@ def workload_name(config, n, d):
         "c3": "C3 GP_binary_classification Laplace N=%d D=%d SE kernel, one Newton iteration" % (n, d),
         "c2": "C2 CO2_example composite kernel N=%d: compute_mar_likelihood + make_prediction(240 test points)" % n,
         "c1": "C1 GP_regression.prediction as shipped N=%d n=100 D=1, 10 posterior draws" % n,
+        "c2p": "C2 CO2_example posterior mean + variance of 2048 test points at N=%d (factor resident, test points sharded)" % n,
     }[config]
 
 
@@ -422,6 +441,41 @@ def make_c2(args, eng, n, D, world, rank, torch):
     return w
 
 
+def make_c2p(args, eng, n, D, world, rank, torch):
+    from gaussian_process_b200 import CO2_example as C2, padded, parallel as P, synthetic as S
+    from gaussian_process_b200._lib import COV_CO2
+    w = Workload()
+    X, y, _ = S.synth_c2(n, 240)
+    m = 2048
+    Xs = X[-1, 0] + (1 + np.arange(m))[:, None] / 12.0
+    th = C2.HYPERMS_BOOK.astype(np.float64)
+    if world > 1:
+        eng.mg_init()
+    fit = eng.mg_fit(COV_CO2, X, y, th, S_NOISE, nb=args.nb)      # distributed fit: the factor is replicated on every rank
+    lo, hi = P.shard_range(m, rank, world)
+    Xs_loc = eng.to_device(Xs[lo:hi])
+    res = {}
+
+    def step():   # this rank's shard of test points, from the replicated factor (no refit, no communication)
+        res["mu"], res["var"], _ = eng.predict(fit, Xs_loc, m_total=m, row0=lo)
+    w.step = step
+
+    def host_step():   # host test points in, all-gathered (mu, var) out on the host
+        res["mu_h"], res["var_h"] = eng.mg_predict(fit, Xs)
+    w.host_step = host_step
+    w.release = lambda: None
+    w.h2d, w.d2h = int(m * D * 8), int(2 * m * 8)
+    npad = float(padded(n))
+    w.alg_flops = npad * npad * padded(m) + 2 * npad * padded(m)
+    w.flops_note = "triangular solve L^-1 K_s for 2048 columns (N^2 m) + the two column reductions"
+    w.parallelism = "single GPU" if world == 1 else "%d ranks, %d test points each, factor replicated by the distributed fit" % (world, hi - lo)
+    w.l2 = "factor (%.2f GB) larger than L2; no flush needed" % (npad * npad * 8 / 1e9)
+    w.timing_handles = (eng,)
+    w.exclusive_kernel_time = False
+    w.finish = lambda: {"lml": fit.lml, "mu0": float(res["mu"][0].item()) if hi > lo else None}
+    return w
+
+
 def make_c3(args, eng, n, D, world, rank, torch):
     from gaussian_process_b200 import padded, synthetic as S
     from gaussian_process_b200 import GP_binary_classification as B
@@ -577,7 +631,7 @@ def make_c1(args, eng, n, D, world, rank, torch):
     return w
 
 
-MAKERS = {"c5": make_c5, "c4": make_c4, "c3": make_c3, "c2": make_c2, "c1": make_c1}
+MAKERS = {"c5": make_c5, "c4": make_c4, "c3": make_c3, "c2": make_c2, "c1": make_c1, "c2p": make_c2p}
 
 
 def run_gpx(args, n, D):
@@ -629,9 +683,13 @@ def run_gpx(args, n, D):
     e1.record()
     barrier()
     if cfg != "c5":           # short timed regions: keep the sampler alive long enough for a few samples under load
-        t_end = time.time() + 1.0
-        while time.time() < t_end:
-            w.step()
+        if world > 1:         # a fixed count on every rank (the steps contain collectives)
+            for _ in range(8):
+                w.step()
+        else:
+            t_end = time.time() + 1.0
+            while time.time() < t_end:
+                w.step()
         torch.cuda.synchronize()
     clocks = sampler.stop()
     ms_total = e0.elapsed_time(e1)

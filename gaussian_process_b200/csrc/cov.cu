@@ -138,7 +138,11 @@ __global__ void __launch_bounds__(CTHREADS) cov_build_kernel(CovParams p_in, con
     }
 }
 
-// grad partials: partial[block][q] = sum over this lower tile of w_ij * dK_ij,q
+// grad partials: partial[block][q] = sum over this lower tile of w_ij * dK_ij,q.
+// The 128 x 128 tile of K^-1 is fetched into shared memory with cp.async at kernel entry and only waited for after the
+// distance loop: the first version loaded it element by element inside the epilogue and spent most of its time in
+// long-scoreboard stalls (ncu: 5.5 stalled warps per issue, FP64 pipe 29 % active, 8 % of DRAM bandwidth).
+constexpr int GRAD_SMEM = TM * TN * (int)sizeof(double);
 template <int KIND>
 __global__ void __launch_bounds__(CTHREADS) lml_grad_kernel(CovParams p_in, const double* __restrict__ X, int64_t n,
                                                            const double* __restrict__ Kinv, int64_t ldk,
@@ -149,6 +153,7 @@ __global__ void __launch_bounds__(CTHREADS) lml_grad_kernel(CovParams p_in, cons
 #pragma unroll
         for (int q = 0; q < NTheta<KIND>::value; ++q) p.th[q] = theta_dev[q];
     }
+    extern __shared__ __align__(16) double ktile[];      // [128][128] tile of K^-1
     __shared__ double xs1[TM * DCH];
     __shared__ double xs2[DCH * TN];
     __shared__ double red[CTHREADS / 32][11];
@@ -162,8 +167,20 @@ __global__ void __launch_bounds__(CTHREADS) lml_grad_kernel(CovParams p_in, cons
     for (int q = 0; q < NTH; ++q) sums[q] = 0.0;
     if (bn <= bm) {
         const int row0 = bm * TM, col0 = bn * TN;
+        {   // 8192 16-byte chunks, 16 per thread, in flight during the whole distance loop
+            const double* src = Kinv + (int64_t)row0 * ldk + col0;
+#pragma unroll
+            for (int c = 0; c < (TM * TN / 2) / CTHREADS; ++c) {
+                const int id = tid + c * CTHREADS, r = id >> 6, c2 = id & 63;
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(ktile + r * TN + 2 * c2);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src + (int64_t)r * ldk + 2 * c2));
+            }
+            asm volatile("cp.async.commit_group;\n" ::);
+        }
         double acc[RI][4], aux[RI][4];
         tile_accumulate<KIND>(p, X, n, X, n, row0, col0, xs1, xs2, acc, aux);
+        asm volatile("cp.async.wait_group 0;\n" ::);
+        __syncthreads();
         const double wmul = (bn == bm) ? 0.5 : 1.0;  // .5 * (1 on diagonal tiles | 2 on strictly-lower tiles)
         double aj[4];
 #pragma unroll
@@ -181,7 +198,7 @@ __global__ void __launch_bounds__(CTHREADS) lml_grad_kernel(CovParams p_in, cons
                 if (r < n && c < n) {
                     double dk[11];
                     (void)cov_eval<KIND, true>(p, acc[i][j], aux[i][j], r == c, dk);
-                    const double w = wmul * (ai * aj[j] - Kinv[r * ldk + c]);
+                    const double w = wmul * (ai * aj[j] - ktile[(ty + 16 * i) * TN + tx + 32 * j]);
 #pragma unroll
                     for (int q = 0; q < NTH; ++q) sums[q] += w * dk[q];
                 }
@@ -337,12 +354,23 @@ int gpx_lml_grad_block(gpx_ctx* h, int kind, const double* X, int64_t n, int D, 
         }
         h->partial_elems = need;
     }
+    {
+        static bool configured_dev[GPX_MAX_DEVICES] = {};
+        bool& configured = configured_dev[h->device % GPX_MAX_DEVICES];   // cudaFuncSetAttribute is per device
+        if (!configured) {
+            GPX_CUDA(cudaFuncSetAttribute(lml_grad_kernel<GPX_COV_SE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAD_SMEM));
+            GPX_CUDA(cudaFuncSetAttribute(lml_grad_kernel<GPX_COV_LIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAD_SMEM));
+            GPX_CUDA(cudaFuncSetAttribute(lml_grad_kernel<GPX_COV_PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAD_SMEM));
+            GPX_CUDA(cudaFuncSetAttribute(lml_grad_kernel<GPX_COV_CO2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAD_SMEM));
+            configured = true;
+        }
+    }
     dim3 grid(ntc, ntr);
     switch (kind) {
-        case GPX_COV_SE: lml_grad_kernel<GPX_COV_SE><<<grid, CTHREADS, 0, h->stream>>>(p, X, n, Kinv, ldk, alpha, h->d_partial, rg0, cg0, theta_dev); break;
-        case GPX_COV_LIN: lml_grad_kernel<GPX_COV_LIN><<<grid, CTHREADS, 0, h->stream>>>(p, X, n, Kinv, ldk, alpha, h->d_partial, rg0, cg0, theta_dev); break;
-        case GPX_COV_PER: lml_grad_kernel<GPX_COV_PER><<<grid, CTHREADS, 0, h->stream>>>(p, X, n, Kinv, ldk, alpha, h->d_partial, rg0, cg0, theta_dev); break;
-        default: lml_grad_kernel<GPX_COV_CO2><<<grid, CTHREADS, 0, h->stream>>>(p, X, n, Kinv, ldk, alpha, h->d_partial, rg0, cg0, theta_dev); break;
+        case GPX_COV_SE: lml_grad_kernel<GPX_COV_SE><<<grid, CTHREADS, GRAD_SMEM, h->stream>>>(p, X, n, Kinv, ldk, alpha, h->d_partial, rg0, cg0, theta_dev); break;
+        case GPX_COV_LIN: lml_grad_kernel<GPX_COV_LIN><<<grid, CTHREADS, GRAD_SMEM, h->stream>>>(p, X, n, Kinv, ldk, alpha, h->d_partial, rg0, cg0, theta_dev); break;
+        case GPX_COV_PER: lml_grad_kernel<GPX_COV_PER><<<grid, CTHREADS, GRAD_SMEM, h->stream>>>(p, X, n, Kinv, ldk, alpha, h->d_partial, rg0, cg0, theta_dev); break;
+        default: lml_grad_kernel<GPX_COV_CO2><<<grid, CTHREADS, GRAD_SMEM, h->stream>>>(p, X, n, Kinv, ldk, alpha, h->d_partial, rg0, cg0, theta_dev); break;
     }
     GPX_CHECK_LAUNCH(h);
     grad_finish_kernel<<<ntheta, 256, 0, h->stream>>>(ntr * ntc, ntheta, h->d_partial, grad);
