@@ -484,11 +484,9 @@ int potrf_la(gpx_ctx* h, double* A, int64_t n, int64_t lda, double* dinv, int go
             if (rc == 0 && cudaEventRecord(evS[j], S) != cudaSuccess) rc = GPX_E_CUDA;
         }
     }
-    // join: S continues only after the chain has finished
-    if (rc == 0) {
-        cudaEventRecord(ev0, H);
-        cudaStreamWaitEvent(S, ev0, 0);
-    }
+    // join: S continues only after the chain has finished -- also on error, so that the caller never recycles A / dinv
+    // while the auxiliary stream is still writing them
+    if (cudaEventRecord(ev0, H) == cudaSuccess) cudaStreamWaitEvent(S, ev0, 0);
     h->stream = S;
     return rc;   // no host synchronisation; EventSet releases the events
 }
@@ -569,12 +567,9 @@ int potrf_la_split(gpx_ctx* h, double* A, int64_t n, int64_t lda, double* dinv, 
             rec(SD, j, S);
         }
     }
-    if (rc == 0) {   // join: S continues only after both chains have finished
-        cudaEventRecord(ev0, H);
-        cudaStreamWaitEvent(S, ev0, 0);
-        cudaEventRecord(ev1, H2);
-        cudaStreamWaitEvent(S, ev1, 0);
-    }
+    // join: S continues only after both chains have finished -- also on error (see potrf_la)
+    if (cudaEventRecord(ev0, H) == cudaSuccess) cudaStreamWaitEvent(S, ev0, 0);
+    if (cudaEventRecord(ev1, H2) == cudaSuccess) cudaStreamWaitEvent(S, ev1, 0);
     h->stream = S;
     return rc;   // no host synchronisation; EventSet releases the events
 }
