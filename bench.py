@@ -350,7 +350,7 @@ def make_c5(args, eng, n, D, world, rank, torch):
     w.alg_flops = float(padded(n)) ** 3            # potrf N^3/3 + trtri N^3/3 + lauum N^3/3
     w.flops_note = "N^3 = potrf + trtri + lauum, N^3/3 each"
     w.parallelism = ("single GPU" if not use_mg else
-                     "1-D block-cyclic block columns (nb=%d) over %d GPU(s), NCCL panel broadcast + all-gather" % (args.nb, world))
+                     "1-D block-cyclic block columns (nb=%d, boustrophedon block->rank map) over %d GPU(s): NCCL panel broadcasts, grouped K=1024 trailing updates, K^-1 by two local prefix TRSMs (no all-gather)" % (args.nb, world))
     w.l2 = "inputs (2 x %.1f GB matrices) larger than L2; no flush needed" % (float(padded(n)) ** 2 * 8 / 1e9)
     w.timing_handles = (eng,)
     w.exclusive_kernel_time = not use_mg     # the recursive single-GPU path runs its big GEMMs on one stream

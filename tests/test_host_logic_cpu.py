@@ -1,6 +1,7 @@
 """CPU tests of the host-side logic of the drop-in modules (no GPU needed): the Bayesian-optimisation layer
 (acquisition functions, candidate samplers, index helpers) against the live reference when /root/reference exists,
 and invariants that hold everywhere.  These functions never touch the engine."""
+import os
 import contextlib
 import io
 import random
@@ -123,3 +124,24 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert "workload" in d["config"] and "N=65536" in d["config"]["workload"]
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm; no GPU needed) prints ONE JSON line with the contract's keys, for the
+    default config and for a per-config metric, also when torchrun's OMP_NUM_THREADS=1 is in the environment."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    for extra, metric in ((["--cpu-sample-n", "256"], "gp_fit_lml_grad_seconds_n65536_fp64"),
+                          (["--config", "c1"], "gp_regression_prediction_seconds_n5_fp64")):
+        out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"] + extra,
+                             capture_output=True, text=True, timeout=600, env=env, cwd=root)
+        assert out.returncode == 0, out.stderr[-1500:]
+        lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+        assert len(lines) == 1
+        d = json.loads(lines[0])
+        assert d["impl"] == "reference" and d["metric"] == metric and d["unit"] == "s" and d["higher_is_better"] is False
+        assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
+        assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["value"] > 0 and "workload" in d["config"]
