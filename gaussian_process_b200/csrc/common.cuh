@@ -142,6 +142,7 @@ int gpx_cov_build_block(gpx_ctx* h, int kind, const double* X, int64_t n, int D,
 int gpx_potrf_block(gpx_ctx* h, double* A, int64_t n, int64_t lda, double* dinv, int goff);
 int gpx_trsm_right_lt_block(gpx_ctx* h, double* B, int64_t m, int64_t ldb, const double* L, int64_t n, int64_t ldl,
                             const double* dinv);
+int gpx_panel_factor_sub(gpx_ctx* h, double* P, int64_t rows, int64_t ld, int nb, double* dinv, int goff);
 int gpx_trsm_left_prefix_block(gpx_ctx* h, const double* L, int64_t n, int64_t ldl, const double* dinv, double* B, int64_t ldb,
                                int P, int p, int nb, int snake, const double* D = nullptr, int bs = 0, double* tmp = nullptr);
 int gpx_trsm_left_prefix_trans_block(gpx_ctx* h, const double* L, int64_t n, int64_t ldl, const double* dinv, double* B,

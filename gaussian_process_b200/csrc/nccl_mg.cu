@@ -103,6 +103,15 @@ int group_k() {   // K of the grouped bulk update
     return g_group_k;
 }
 
+int panel_sub() {   // 1 (default): panels factored by the substitution chain; 0: potrf + GEMM-based TRSM (round-2 baseline)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GPX_MG_PANEL_SUB");
+        v = e ? atoi(e) : 1;
+    }
+    return v;
+}
+
 int g_snake = -1;
 int layout_snake() {   // 1: boustrophedon block -> rank map (default), 0: plain block-cyclic
     if (g_snake < 0) {
@@ -148,9 +157,13 @@ int panel_factor_pack(MgRank& r, int64_t j, double* stage) {
     const int64_t q = gpx_cyc_local(j, r.P, r.snake), r0 = j * r.nb, rows = r.npad - r0;
     double* diag = r.Aloc + r0 * r.wloc + q * r.nb;
     double* dinvj = r.dinv + j * r.tpb * GPX_T * GPX_T;
-    GPX_TRY(gpx_potrf_block(h, diag, r.nb, r.wloc, dinvj, (int)r0));
-    if (rows > r.nb)
-        GPX_TRY(gpx_trsm_right_lt_block(h, diag + (int64_t)r.nb * r.wloc, rows - r.nb, r.wloc, diag, r.nb, r.wloc, dinvj));
+    if (panel_sub()) {
+        GPX_TRY(gpx_panel_factor_sub(h, diag, rows, r.wloc, r.nb, dinvj, (int)r0));   // substitution chain (see potrf.cu)
+    } else {
+        GPX_TRY(gpx_potrf_block(h, diag, r.nb, r.wloc, dinvj, (int)r0));
+        if (rows > r.nb)
+            GPX_TRY(gpx_trsm_right_lt_block(h, diag + (int64_t)r.nb * r.wloc, rows - r.nb, r.wloc, diag, r.nb, r.wloc, dinvj));
+    }
     GPX_CUDA(cudaMemcpy2DAsync(stage, r.nb * sizeof(double), diag, r.wloc * sizeof(double), r.nb * sizeof(double), rows,
                                cudaMemcpyDeviceToDevice, h->stream));
     GPX_CUDA(cudaMemcpyAsync(stage + (size_t)rows * r.nb, dinvj, (size_t)r.tpb * GPX_T * GPX_T * sizeof(double),

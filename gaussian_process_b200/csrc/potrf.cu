@@ -11,6 +11,7 @@
 // Replaces np.linalg.cholesky / np.linalg.solve(L, .) / np.linalg.inv(L) / np.dot(inv(L.T), inv(L))
 // (SURVEY.md 8a rows A4, A5).
 #include <stdlib.h>
+#include <algorithm>
 #include <vector>
 #include "common.cuh"
 
@@ -32,13 +33,14 @@ constexpr int LEAF_SMEM = (NBK * 578 + LT) * (int)sizeof(double);
 // info: first failing pivot (global 1-based index) is recorded once.
 // 4x4 blocks are stored block-major with 16-byte skews (block = 18 doubles, block row = 578 doubles) so that a warp whose
 // lanes read the same chunk of 32 different blocks -- along a block row or a block column -- hits distinct bank groups.
-__device__ __forceinline__ int soff(int a, int b) { return (a >> 2) * 578 + (b >> 2) * 18 + (a & 3) * 4 + (b & 3); }
+__device__ __forceinline__ int soff_full(int a, int b) { return (a >> 2) * 578 + (b >> 2) * 18 + (a & 3) * 4 + (b & 3); }
 __device__ long long g_leaf_dbg[8];
-__global__ void __launch_bounds__(LEAF_THREADS, 1)
-potrf_leaf_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ Dinv, int* info, int global_off,
-                  int64_t strideA, int64_t strideD) {
-    extern __shared__ __align__(16) double sm[];
-    __shared__ int fail_col;
+// MODE 0: factor + inverse (A <- L, Dinv <- L^-1); MODE 1: factor only (the look-ahead chain: the explicit inverse is taken
+// off the critical path and formed later by one batched MODE 2 launch); MODE 2: inverse only (A holds L, Dinv <- L^-1).
+template <int MODE>
+__device__ __forceinline__ void potrf_leaf_body(double* __restrict__ A, int64_t lda, double* __restrict__ Dinv, int* info,
+                                                int global_off, int64_t strideA, int64_t strideD, double* sm, int& fail_col) {
+    auto soff = [](int a, int b) -> int { return soff_full(a, b); };
     double* S = sm;
     double* dd = sm + NBK * 578;
     A += (int64_t)blockIdx.x * strideA;
@@ -72,6 +74,39 @@ potrf_leaf_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ Dinv
         }
     }
     if (tid == 0) fail_col = -1;
+    if (MODE == 2 && active) {
+        // inverse only: the block just loaded IS the factor.  S(lower + diag) <- L, and every diagonal thread forms its
+        // X_pp = L_pp^-1 (4x4, in registers) -> S(strict upper of the diagonal block) = X_pp^T, dd = diag(X_pp).
+        if (bi == bj) {
+            double x[LB][LB];
+#pragma unroll
+            for (int c = 0; c < LB; ++c) x[c][c] = 1.0 / a[c][c];
+#pragma unroll
+            for (int c = 0; c < LB; ++c)
+#pragma unroll
+                for (int r = c + 1; r < LB; ++r) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int m = c; m < r; ++m) v += a[r][m] * x[m][c];
+                    x[r][c] = -v * x[r][r];
+                }
+#pragma unroll
+            for (int r = 0; r < LB; ++r) {
+                dd[LB * bi + r] = x[r][r];
+#pragma unroll
+                for (int c = 0; c <= r; ++c) S[soff(LB * bi + r, LB * bi + c)] = a[r][c];
+#pragma unroll
+                for (int c = 0; c < r; ++c) S[soff(LB * bi + c, LB * bi + r)] = x[r][c];
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < LB; ++r) {
+                double2* dst = reinterpret_cast<double2*>(S + soff(LB * bi + r, LB * bj));
+                dst[0] = make_double2(a[r][0], a[r][1]);
+                dst[1] = make_double2(a[r][2], a[r][3]);
+            }
+        }
+    }
     __syncthreads();
     const long long t_loaded = clock64();
 
@@ -167,6 +202,7 @@ potrf_leaf_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ Dinv
                 for (int c = 0; c < LB; ++c) a[r][c] = fma(-li[r][m], lj[c][m], a[r][c]);
     };
 
+    if (MODE != 2) {
     if (active && bi == 0 && bj == 0) diag_factor(0);
     __syncthreads();
     if (fail_col < 0) {
@@ -190,7 +226,15 @@ potrf_leaf_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ Dinv
         for (int idx = tid; idx < LT * LT; idx += LEAF_THREADS) {
             int i = idx >> 7, j = idx & 127;
             A[(int64_t)i * lda + j] = (j <= i) ? qnan : 0.0;
-            Dinv[idx] = (j <= i) ? qnan : 0.0;
+            if (MODE == 0) Dinv[idx] = (j <= i) ? qnan : 0.0;
+        }
+        return;
+    }
+    }   // MODE != 2
+    if (MODE == 1) {   // factor only: store L (upper triangle zeroed) and leave
+        for (int idx = tid; idx < LT * LT; idx += LEAF_THREADS) {
+            int i = idx >> 7, j = idx & 127;
+            A[(int64_t)i * lda + j] = (j <= i) ? S[soff(i, j)] : 0.0;
         }
         return;
     }
@@ -263,7 +307,7 @@ potrf_leaf_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ Dinv
     const long long t_inv = clock64();
     for (int idx = tid; idx < LT * LT; idx += LEAF_THREADS) {
         int i = idx >> 7, j = idx & 127;
-        A[(int64_t)i * lda + j] = (j <= i) ? S[soff(i, j)] : 0.0;
+        if (MODE == 0) A[(int64_t)i * lda + j] = (j <= i) ? S[soff(i, j)] : 0.0;
         Dinv[idx] = (j < i) ? S[soff(j, i)] : (j == i ? dd[i] : 0.0);
     }
     if (tid == 0 && blockIdx.x == 0) {
@@ -274,6 +318,14 @@ potrf_leaf_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ Dinv
     }
 }
 
+template <int MODE>
+__global__ void __launch_bounds__(LEAF_THREADS, 1)
+potrf_leaf_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ Dinv, int* info, int global_off,
+                  int64_t strideA, int64_t strideD) {
+    extern __shared__ __align__(16) double sm[];
+    __shared__ int fail_col;
+    potrf_leaf_body<MODE>(A, lda, Dinv, info, global_off, strideA, strideD, sm, fail_col);
+}
 __global__ void zero_upper_tiles_kernel(double* A, int64_t lda, int nt) {
     // grid (nt, nt): zero tile (bi, bj) for bj > bi
     int bi = blockIdx.y, bj = blockIdx.x;
@@ -285,18 +337,80 @@ __global__ void zero_upper_tiles_kernel(double* A, int64_t lda, int nt) {
     }
 }
 
+// mode 0: factor + inverse; 1: factor only; 2: inverse only (see potrf_leaf_kernel)
 int leaf(gpx_ctx* h, double* A, int64_t lda, double* dinv_tile, int goff, int batch = 1, int64_t strideA = 0,
-         int64_t strideD = 0) {
+         int64_t strideD = 0, int mode = 0) {
     static bool configured_dev[GPX_MAX_DEVICES] = {};
     bool& configured = configured_dev[h->device % GPX_MAX_DEVICES];   // cudaFuncSetAttribute is per device
     if (!configured) {
-        GPX_CUDA(cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM));
+        GPX_CUDA(cudaFuncSetAttribute(potrf_leaf_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM));
+        GPX_CUDA(cudaFuncSetAttribute(potrf_leaf_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM));
+        GPX_CUDA(cudaFuncSetAttribute(potrf_leaf_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM));
         configured = true;
     }
     gpx_timing_leaf_begin(h);
-    potrf_leaf_kernel<<<batch, LEAF_THREADS, LEAF_SMEM, h->stream>>>(A, lda, dinv_tile, h->d_info, goff, strideA, strideD);
+    if (mode == 1) potrf_leaf_kernel<1><<<batch, LEAF_THREADS, LEAF_SMEM, h->stream>>>(A, lda, dinv_tile, h->d_info, goff, strideA, strideD);
+    else if (mode == 2) potrf_leaf_kernel<2><<<batch, LEAF_THREADS, LEAF_SMEM, h->stream>>>(A, lda, dinv_tile, h->d_info, goff, strideA, strideD);
+    else potrf_leaf_kernel<0><<<batch, LEAF_THREADS, LEAF_SMEM, h->stream>>>(A, lda, dinv_tile, h->d_info, goff, strideA, strideD);
     GPX_CHECK_LAUNCH(h);
     gpx_timing_leaf_end(h);
+    return 0;
+}
+
+// ---- X L^T = B in place for ONE 128 x 128 lower-triangular leaf L (row-major, ldl), any number of rows of B: forward
+// substitution, one WARP per row (the row lives in registers, 4 entries per lane), L^T packed in shared memory, no
+// barrier inside the 128 steps (one multiply, one shuffle, up to four FMAs each).  ~7 us for up to 4736 rows: this is the
+// TRSM of the look-ahead chain, which so far had to wait for the explicit inverse of the leaf (27 us) and then ran as a GEMM.
+constexpr int TS_WARPS = 32;
+constexpr int TS_SMEM = (LT * (LT + 1) / 2 + LT) * (int)sizeof(double);
+__global__ void __launch_bounds__(TS_WARPS * 32) trsm_sub_kernel(double* __restrict__ B, int64_t ldb, int64_t rows,
+                                                                  const double* __restrict__ L, int64_t ldl) {
+    extern __shared__ __align__(16) double tsm[];
+    double* U = tsm;                          // U[off(m) + (k - m)] = L[k][m], k >= m : column m of L from the diagonal down
+    double* rd = tsm + LT * (LT + 1) / 2;     // 1 / L[m][m]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int idx = tid; idx < LT * LT; idx += TS_WARPS * 32) {
+        const int k = idx >> 7, m = idx & 127;
+        if (m <= k) U[m * LT - (m * (m - 1)) / 2 + (k - m)] = L[(int64_t)k * ldl + m];
+    }
+    if (tid < LT) rd[tid] = 1.0 / L[(int64_t)tid * ldl + tid];
+    __syncthreads();
+    const int64_t r = (int64_t)blockIdx.x * TS_WARPS + warp;
+    if (r >= rows) return;
+    double* row = B + r * ldb;
+    double a[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = row[lane + 32 * i];
+#pragma unroll
+    for (int slot = 0; slot < 4; ++slot) {
+#pragma unroll 8
+        for (int mm = 0; mm < 32; ++mm) {
+            const int m = slot * 32 + mm;
+            const double* u = U + (m * LT - (m * (m - 1)) / 2) - m;   // u[k] = L[k][m]
+            const double xm = __shfl_sync(0xffffffffu, a[slot] * rd[m], mm);
+            if (lane == mm) a[slot] = xm;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (i < slot) continue;
+                const int k = lane + 32 * i;
+                if (k > m) a[i] = fma(-xm, u[k], a[i]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) row[lane + 32 * i] = a[i];
+}
+
+int trsm_sub(gpx_ctx* h, double* B, int64_t rows, int64_t ldb, const double* L, int64_t ldl) {
+    if (rows <= 0) return 0;
+    static bool configured_dev[GPX_MAX_DEVICES] = {};
+    bool& configured = configured_dev[h->device % GPX_MAX_DEVICES];
+    if (!configured) {
+        GPX_CUDA(cudaFuncSetAttribute(trsm_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
+        configured = true;
+    }
+    trsm_sub_kernel<<<(unsigned)((rows + TS_WARPS - 1) / TS_WARPS), TS_WARPS * 32, TS_SMEM, h->stream>>>(B, ldb, rows, L, ldl);
+    GPX_CHECK_LAUNCH(h);
     return 0;
 }
 
@@ -426,8 +540,11 @@ namespace {
 //   bulk stream S                 : update block columns >= j+3 with panel j
 // so the latency-bound panel chain runs concurrently with (and up to two panels ahead of) the DMMA-bound bulk updates.
 int potrf_la_split(gpx_ctx* h, double* A, int64_t n, int64_t lda, double* dinv, int goff, int nb);
+int potrf_la_grouped(gpx_ctx* h, double* A, int64_t n, int64_t lda, double* dinv, int goff, int G);
 int la_split();
+int la_group(int64_t n);
 int potrf_la(gpx_ctx* h, double* A, int64_t n, int64_t lda, double* dinv, int goff, int nb) {
+    if (la_split() && h->aux2_stream && nb == LT && la_group(n) > 1) return potrf_la_grouped(h, A, n, lda, dinv, goff, la_group(n));
     if (la_split() && h->aux2_stream) return potrf_la_split(h, A, n, lda, dinv, goff, nb);
     const int64_t nblk = n / nb;
     const int tpb = nb / LT;
@@ -532,26 +649,37 @@ int potrf_la_split(gpx_ctx* h, double* A, int64_t n, int64_t lda, double* dinv, 
         a.lower_only = lower;
         return gpx_gemm_launch(h, a);
     };
-    on(H, [&]() { return potrf_rec(h, blk(0, 0), nb, lda, dj(0), goff); });
+    // nb == 128: the chain factors leaves WITHOUT their explicit inverses and solves by substitution (trsm_sub); the
+    // inverses every later solve needs are formed by one batched launch after the factorisation (off the critical path).
+    const bool sub = (nb == LT);
+    auto factor_diag = [&](int64_t j) -> int {
+        if (sub) return leaf(h, blk(j, j), lda, dj(j), goff + (int)(j * nb), 1, 0, 0, 1);
+        return potrf_rec(h, blk(j, j), nb, lda, dj(j), goff + (int)(j * nb));
+    };
+    auto panel_trsm = [&](int64_t i0, int64_t rows, int64_t j) -> int {
+        if (sub) return trsm_sub(h, blk(i0, j), rows, lda, blk(j, j), lda);
+        return trsm_right_lt(h, blk(i0, j), rows, lda, blk(j, j), nb, lda, dj(j));
+    };
+    on(H, [&]() { return factor_diag(0); });
     rec(LEAF, 0, H);
     for (int64_t j = 0; j < nblk && rc == 0; ++j) {
         const int64_t rest = nblk - (j + 2);       // block rows below block row j+1
         // ---- H: the part of panel j the next diagonal block waits for
         if (j + 1 < nblk) {
             wait(H, U1, j - 1); wait(H, U2, j - 2); wait(H, SD, j - 3);          // block (j+1, j) has every earlier update
-            on(H, [&]() { return trsm_right_lt(h, blk(j + 1, j), nb, lda, blk(j, j), nb, lda, dj(j)); });
+            on(H, [&]() { return panel_trsm(j + 1, nb, j); });
             rec(TOP, j, H);
             wait(H, U2, j - 1); wait(H, SD, j - 2);                              // block (j+1, j+1) likewise
             on(H, [&]() {
                 GPX_TRY(update(j, j + 1, 1, j + 1, 1, 1));
-                return potrf_rec(h, blk(j + 1, j + 1), nb, lda, dj(j + 1), goff + (int)((j + 1) * nb));
+                return factor_diag(j + 1);
             });
             rec(LEAF, j + 1, H);
         }
         // ---- H2: the rest of column j, then its updates of columns j+1 and j+2
         if (rest > 0) {
             wait(H2, LEAF, j); wait(H2, SD, j - 3);
-            on(H2, [&]() { return trsm_right_lt(h, blk(j + 2, j), rest * nb, lda, blk(j, j), nb, lda, dj(j)); });
+            on(H2, [&]() { return panel_trsm(j + 2, rest * nb, j); });
             rec(PAN, j, H2);
             wait(H2, TOP, j); wait(H2, SD, j - 2);
             on(H2, [&]() { return update(j, j + 2, rest, j + 1, 1, 0); });
@@ -571,7 +699,125 @@ int potrf_la_split(gpx_ctx* h, double* A, int64_t n, int64_t lda, double* dinv, 
     if (cudaEventRecord(ev0, H) == cudaSuccess) cudaStreamWaitEvent(S, ev0, 0);
     if (cudaEventRecord(ev1, H2) == cudaSuccess) cudaStreamWaitEvent(S, ev1, 0);
     h->stream = S;
+    if (rc == 0 && sub)   // all leaf inverses in ONE batched launch (nblk CTAs, ~27 us)
+        rc = leaf(h, A, lda, dinv, goff, (int)nblk, (int64_t)nb * (lda + 1), (int64_t)LT * LT, 2);
     return rc;   // no host synchronisation; EventSet releases the events
+}
+
+
+// The look-ahead factorisation with GROUPED bulk updates (the single-GPU twin of the multi-GPU driver's scheme): 128-wide
+// panels for the chain, but the bulk of the trailing matrix is updated once per group of G panels with K = G*128, where the
+// DMMA GEMM runs near its large-K rate (a K = 128 update reaches ~25 TF).  For panel j of group g = j / G:
+//   H  (chain, high priority): TOP(j): block (j+1, j) <- . L_jj^-T by substitution;  [j+1 in the same group:] diagonal
+//                              block (j+1, j+1) -= L(j+1,j) L(j+1,j)^T, factor it (no inverse)
+//   H2 (column work)         : PAN(j): rows >= j+2 of column j by substitution;  U1: column j+1, U2: column j+2,
+//                              E: columns j+3 .. end of the group (all K = 128, inside the group only)
+//   S  (bulk)                : when the group is complete  A(g): the NEXT group's columns (K = G*128; the chain of group
+//                              g+1 waits for it), then B(g): all columns beyond the next group (K = G*128) -- B(g) overlaps
+//                              with the chain of group g+1.
+// Every block receives the contributions of all earlier panels exactly once (own-group panels eagerly, earlier groups in
+// A / B), in a fixed order, so the result does not depend on timing.
+int potrf_la_grouped(gpx_ctx* h, double* A, int64_t n, int64_t lda, double* dinv, int goff, int G) {
+    constexpr int nb = LT;
+    const int64_t nblk = n / nb;
+    const int64_t ngrp = (nblk + G - 1) / G;
+    cudaStream_t S = h->stream, H = h->aux_stream, H2 = h->aux2_stream;
+    enum { LEAF = 0, TOP, PAN, U1, U2, AG, NEV };
+    GpxEventSet es;
+    GPX_TRY(es.create(NEV * nblk + 2));
+    auto E = [&](int kind, int64_t j) -> cudaEvent_t { return es.ev[kind * nblk + j]; };
+    int rc = 0;
+    auto rec = [&](int kind, int64_t j, cudaStream_t st) { if (rc == 0 && cudaEventRecord(E(kind, j), st) != cudaSuccess) rc = GPX_E_CUDA; };
+    auto wait = [&](cudaStream_t st, int kind, int64_t j) { if (rc == 0 && j >= 0 && cudaStreamWaitEvent(st, E(kind, j), 0) != cudaSuccess) rc = GPX_E_CUDA; };
+    auto on = [&](cudaStream_t st, auto&& fn) { if (rc != 0) return; h->stream = st; rc = fn(); h->stream = S; };
+    cudaEvent_t ev0 = es.ev[NEV * nblk], ev1 = es.ev[NEV * nblk + 1];
+    GPX_CUDA(cudaEventRecord(ev0, S));            // everything queued on S so far precedes the factorisation
+    GPX_CUDA(cudaStreamWaitEvent(H, ev0, 0));
+    GPX_CUDA(cudaStreamWaitEvent(H2, ev0, 0));
+    auto blk = [&](int64_t i, int64_t j) -> double* { return A + i * nb * lda + j * nb; };
+    // C(block rows r0.., block columns c..c+ncols) -= A(rows r0.., panels j..j+np) * A(block rows c.., panels j..j+np)^T
+    auto update = [&](int64_t j, int64_t np, int64_t r0, int64_t rows, int64_t c, int64_t ncols, int lower) -> int {
+        if (rows <= 0 || ncols <= 0 || np <= 0) return 0;
+        GemmArgs a = base_args();
+        a.A = blk(r0, j); a.lda = lda; a.a_kmajor = 1;
+        a.B = blk(c, j); a.ldb = lda; a.b_kmajor = 1;
+        a.C = blk(r0, c); a.ldc = lda;
+        a.M = (int)(rows * nb); a.N = (int)(ncols * nb); a.K = (int)(np * nb);
+        a.alpha = -1.0; a.beta = 1.0;
+        a.lower_only = lower;
+        return gpx_gemm_launch(h, a);
+    };
+    auto factor_diag = [&](int64_t j) -> int { return leaf(h, blk(j, j), lda, dinv + j * LT * LT, goff + (int)(j * nb), 1, 0, 0, 1); };
+    on(H, [&]() { return factor_diag(0); });
+    rec(LEAF, 0, H);
+    for (int64_t j = 0; j < nblk && rc == 0; ++j) {
+        const int64_t g = j / G, gend = std::min<int64_t>((g + 1) * G, nblk);     // this group's columns are [g*G, gend)
+        const bool next_in_group = j + 1 < gend;
+        // ---- H: block row j+1 of panel j, then (inside the group) the next diagonal block
+        if (j + 1 < nblk) {
+            if (j > g * G) wait(H, U1, j - 1);                                   // block (j+1, j) has every in-group update
+            on(H, [&]() { return trsm_sub(h, blk(j + 1, j), nb, lda, blk(j, j), lda); });
+            rec(TOP, j, H);
+            if (next_in_group) {
+                if (j > g * G) wait(H, U2, j - 1);                               // block (j+1, j+1) likewise (U2 of panel j-1)
+                on(H, [&]() {
+                    GPX_TRY(update(j, 1, j + 1, 1, j + 1, 1, 1));
+                    return factor_diag(j + 1);
+                });
+                rec(LEAF, j + 1, H);
+            }
+        }
+        // ---- H2: the rest of column j, then its updates of the remaining columns of the group
+        const int64_t rest = nblk - (j + 2);
+        if (rest > 0) {
+            wait(H2, LEAF, j);
+            on(H2, [&]() { return trsm_sub(h, blk(j + 2, j), rest * nb, lda, blk(j, j), lda); });
+            rec(PAN, j, H2);
+            if (next_in_group) {
+                wait(H2, TOP, j);
+                on(H2, [&]() { return update(j, 1, j + 2, rest, j + 1, 1, 0); });                       // column j+1, rows >= j+2
+                rec(U1, j, H2);
+                if (j + 2 < gend) {
+                    on(H2, [&]() { return update(j, 1, j + 2, rest, j + 2, 1, 1); });                   // column j+2
+                    rec(U2, j, H2);
+                    if (j + 3 < gend)
+                        on(H2, [&]() { return update(j, 1, j + 3, nblk - (j + 3), j + 3, gend - (j + 3), 1); });   // rest of the group
+                } else {
+                    rec(U2, j, H2);
+                }
+            }
+        }
+        // ---- S: the group is complete -> A(g) on the next group's columns, then the deferred bulk B(g)
+        if (j + 1 == gend && gend < nblk) {
+            const int64_t g0 = g * G, np = gend - g0;
+            const int64_t nend = std::min<int64_t>(gend + G, nblk);              // next group's columns [gend, nend)
+            if (rest > 0) wait(S, PAN, j);
+            wait(S, TOP, j);
+            on(S, [&]() { return update(g0, np, gend, nblk - gend, gend, nend - gend, 1); });
+            rec(AG, g, S);
+            wait(H, AG, g);
+            on(H, [&]() { return factor_diag(gend); });
+            rec(LEAF, gend, H);
+            if (nend < nblk) on(S, [&]() { return update(g0, np, nend, nblk - nend, nend, nblk - nend, 1); });
+        }
+    }
+    (void)ngrp;
+    if (cudaEventRecord(ev0, H) == cudaSuccess) cudaStreamWaitEvent(S, ev0, 0);
+    if (cudaEventRecord(ev1, H2) == cudaSuccess) cudaStreamWaitEvent(S, ev1, 0);
+    h->stream = S;
+    if (rc == 0)   // all leaf inverses in ONE batched launch (nblk CTAs, ~27 us)
+        rc = leaf(h, A, lda, dinv, goff, (int)nblk, (int64_t)nb * (lda + 1), (int64_t)LT * LT, 2);
+    return rc;
+}
+
+int la_group(int64_t n) {   // panels per group of the grouped look-ahead factorisation (0 / 1: ungrouped potrf_la_split)
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("GPX_POTRF_LA_GROUP");
+        forced = e ? atoi(e) : 0;
+    }
+    if (forced > 0) return forced;
+    return n <= 2048 ? 1 : (n <= 4096 ? 2 : (n <= 8192 ? 4 : 8));
 }
 
 int la_split() {   // 1: potrf_la_split (default), 0: potrf_la
@@ -590,7 +836,7 @@ int la_block(int64_t n) {   // panel width of the look-ahead algorithm
         forced = e ? atoi(e) : 0;
     }
     if (forced > 0) return forced;
-    return n <= 8192 ? 128 : 256;
+    return la_split() ? 128 : (n <= 8192 ? 128 : 256);   // the substitution chain (potrf_la_split) works on 128-wide panels
 }
 
 int la_threshold() {   // largest n factored by the look-ahead algorithm (0 disables it)
@@ -758,6 +1004,32 @@ int gpx_potrf_block(gpx_ctx* h, double* A, int64_t n, int64_t lda, double* dinv,
 int gpx_trsm_right_lt_block(gpx_ctx* h, double* B, int64_t m, int64_t ldb, const double* L, int64_t n, int64_t ldl,
                             const double* dinv) {
     return trsm_right_lt(h, B, m, ldb, L, n, ldl, dinv);
+}
+
+// One whole panel of the multi-GPU driver (nb columns, `rows` rows from the diagonal block down, leading dimension ld):
+// leaf by leaf -- factor the 128 x 128 diagonal leaf WITHOUT its inverse, solve everything below it by substitution
+// (warp per row), update the remaining columns of the panel (K = 128) -- and the leaf inverses in one batched launch at the
+// end.  Replaces potrf(nb) + a GEMM-based TRSM against explicit inverses (three K = 128 launches over the full height).
+int gpx_panel_factor_sub(gpx_ctx* h, double* P, int64_t rows, int64_t ld, int nb, double* dinv, int goff) {
+    const int tpb = nb / LT;
+    for (int t = 0; t < tpb; ++t) {
+        double* D = P + (int64_t)t * LT * ld + t * LT;                       // diagonal leaf t
+        GPX_TRY(leaf(h, D, ld, dinv + (int64_t)t * LT * LT, goff + t * LT, 1, 0, 0, 1));
+        const int64_t below = rows - (int64_t)(t + 1) * LT;
+        if (below <= 0) continue;
+        GPX_TRY(trsm_sub(h, D + (int64_t)LT * ld, below, ld, D, ld));
+        if (t + 1 < tpb) {
+            GemmArgs a = base_args();  // columns (t+1)*128 .. nb of the panel -= P_t P_t^T (rows below leaf t)
+            a.A = D + (int64_t)LT * ld; a.lda = ld; a.a_kmajor = 1;
+            a.B = a.A; a.ldb = ld; a.b_kmajor = 1;
+            a.C = D + (int64_t)LT * ld + LT; a.ldc = ld;
+            a.M = (int)below; a.N = (tpb - 1 - t) * LT; a.K = LT;
+            a.alpha = -1.0; a.beta = 1.0;
+            a.lower_only = 1;
+            GPX_TRY(gpx_gemm_launch(h, a));
+        }
+    }
+    return leaf(h, P, ld, dinv, goff, tpb, (int64_t)LT * (ld + 1), (int64_t)LT * LT, 2);
 }
 
 namespace {
