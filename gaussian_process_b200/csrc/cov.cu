@@ -16,13 +16,62 @@ using namespace gpx_cov;
 
 constexpr int TM = 128, TN = 128, DCH = 16, CTHREADS = 512, RI = 8;  // thread owns RI x 4 outputs
 
+// One chunk of DC coordinates of a 128x128 tile: stage the X tiles in shared memory and accumulate.  DC > 0 is a compile-time
+// chunk width (index arithmetic by shifts, the coordinate loop fully unrolled: the runtime-width loop spent 40 % of its issue
+// slots on UMOV / IMAD / ISETP / BRA and an integer division per staged element -- ncu source page, round 2); DC == 0 is the
+// generic runtime-width fallback.
+template <int KIND, int DC>
+__device__ __forceinline__ void tile_chunk(const CovParams& p, const double* __restrict__ X1, int64_t n1,
+                                           const double* __restrict__ X2, int64_t n2, int row0, int col0, int d0, int dc_rt,
+                                           double* xs1, double* xs2, double (&acc)[RI][4], double (&aux)[RI][4]) {
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const int D = p.D;
+    const int dc = DC > 0 ? DC : dc_rt;
+    __syncthreads();
+    for (int idx = tid; idx < TM * dc; idx += CTHREADS) {
+        const int r = DC > 0 ? idx / DC : idx / dc, dd = idx - r * dc;
+        const int64_t gr = row0 + r;
+        xs1[r * DCH + dd] = gr < n1 ? X1[gr * D + d0 + dd] : 0.0;
+    }
+    for (int idx = tid; idx < TN * dc; idx += CTHREADS) {
+        const int c = DC > 0 ? idx / DC : idx / dc, dd = idx - c * dc;
+        const int64_t gc = col0 + c;
+        xs2[dd * TN + c] = gc < n2 ? X2[gc * D + d0 + dd] : 0.0;
+    }
+    __syncthreads();
+    auto body = [&](int dd) {
+        double b[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = xs2[dd * TN + tx + 32 * j];
+#pragma unroll
+        for (int i = 0; i < RI; ++i) {
+            const double a = xs1[(ty + 16 * i) * DCH + dd];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (KIND == GPX_COV_LIN) {
+                    acc[i][j] += (a - p.th[0]) * (b[j] - p.th[0]);
+                    aux[i][j] += a + b[j];
+                } else {
+                    const double df = a - b[j];
+                    acc[i][j] += df * df;
+                }
+            }
+        }
+    };
+    if (DC > 0) {
+#pragma unroll
+        for (int dd = 0; dd < (DC > 0 ? DC : 1); ++dd) body(dd);
+    } else {
+        for (int dd = 0; dd < dc; ++dd) body(dd);
+    }
+}
+
 // Accumulate pairwise terms for a 128x128 tile: thread (tx = tid&31, ty = tid>>5) owns rows ty+16i (i<8)
 // and columns tx+32j (j<4).  xs1: [128][DCH] row tile, xs2: [DCH][128] transposed column tile.
 template <int KIND>
 __device__ __forceinline__ void tile_accumulate(const CovParams& p, const double* __restrict__ X1, int64_t n1,
                                                 const double* __restrict__ X2, int64_t n2, int row0, int col0,
                                                 double* xs1, double* xs2, double (&acc)[RI][4], double (&aux)[RI][4]) {
-    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
     const int D = p.D;
 #pragma unroll
     for (int i = 0; i < RI; ++i)
@@ -30,37 +79,10 @@ __device__ __forceinline__ void tile_accumulate(const CovParams& p, const double
         for (int j = 0; j < 4; ++j) acc[i][j] = aux[i][j] = 0.0;
     for (int d0 = 0; d0 < D; d0 += DCH) {
         const int dc = (D - d0) < DCH ? (D - d0) : DCH;
-        __syncthreads();
-        for (int idx = tid; idx < TM * dc; idx += CTHREADS) {
-            int r = idx / dc, dd = idx - r * dc;
-            int64_t gr = row0 + r;
-            xs1[r * DCH + dd] = gr < n1 ? X1[gr * D + d0 + dd] : 0.0;
-        }
-        for (int idx = tid; idx < TN * dc; idx += CTHREADS) {
-            int c = idx / dc, dd = idx - c * dc;
-            int64_t gc = col0 + c;
-            xs2[dd * TN + c] = gc < n2 ? X2[gc * D + d0 + dd] : 0.0;
-        }
-        __syncthreads();
-        for (int dd = 0; dd < dc; ++dd) {
-            double b[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = xs2[dd * TN + tx + 32 * j];
-#pragma unroll
-            for (int i = 0; i < RI; ++i) {
-                const double a = xs1[(ty + 16 * i) * DCH + dd];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (KIND == GPX_COV_LIN) {
-                        acc[i][j] += (a - p.th[0]) * (b[j] - p.th[0]);
-                        aux[i][j] += a + b[j];
-                    } else {
-                        const double df = a - b[j];
-                        acc[i][j] += df * df;
-                    }
-                }
-            }
-        }
+        if (dc == 16) tile_chunk<KIND, 16>(p, X1, n1, X2, n2, row0, col0, d0, dc, xs1, xs2, acc, aux);
+        else if (dc == 8) tile_chunk<KIND, 8>(p, X1, n1, X2, n2, row0, col0, d0, dc, xs1, xs2, acc, aux);
+        else if (dc == 1) tile_chunk<KIND, 1>(p, X1, n1, X2, n2, row0, col0, d0, dc, xs1, xs2, acc, aux);
+        else tile_chunk<KIND, 0>(p, X1, n1, X2, n2, row0, col0, d0, dc, xs1, xs2, acc, aux);
     }
 }
 
