@@ -105,14 +105,17 @@ int group_k() {   // K of the grouped bulk update
 
 // Panels factored by the substitution chain (gpx_panel_factor_sub) or by potrf + GEMM-based TRSM?  Measured at 8 GPUs: the
 // substitution chain wins where the factorisation is chain-bound (C3, N = 16384: 41.1 -> 38.5 ms per Newton step) and is
-// level / slightly behind where the panels are tall (C5, N = 65536: 1.162 vs 1.166 s) -> default by size; $GPX_MG_PANEL_SUB forces it.
-int panel_sub(int64_t npad) {
-    static int v = -2;
+// level / slightly behind where the panels are tall (C5, N = 65536: 1.162 vs 1.166 s) -> default by problem size and, inside a
+// large factorisation, by panel height (the short panels of the chain-bound tail); $GPX_MG_PANEL_SUB forces it.
+int panel_sub(int64_t npad, int64_t rows) {   // rows = height of this panel
+    static int v = -2, tall = -1;
     if (v == -2) {
         const char* e = getenv("GPX_MG_PANEL_SUB");
         v = e ? atoi(e) : -1;
+        const char* t = getenv("GPX_MG_PANEL_SUB_ROWS");   // panels at most this tall use the substitution chain
+        tall = t ? atoi(t) : 24576;
     }
-    return v >= 0 ? v : (npad <= 32768 ? 1 : 0);
+    return v >= 0 ? v : ((npad <= 32768 || rows <= tall) ? 1 : 0);
 }
 
 int g_snake = -1;
@@ -160,7 +163,7 @@ int panel_factor_pack(MgRank& r, int64_t j, double* stage) {
     const int64_t q = gpx_cyc_local(j, r.P, r.snake), r0 = j * r.nb, rows = r.npad - r0;
     double* diag = r.Aloc + r0 * r.wloc + q * r.nb;
     double* dinvj = r.dinv + j * r.tpb * GPX_T * GPX_T;
-    if (panel_sub(r.npad)) {
+    if (panel_sub(r.npad, rows)) {
         GPX_TRY(gpx_panel_factor_sub(h, diag, rows, r.wloc, r.nb, dinvj, (int)r0));   // substitution chain (see potrf.cu)
     } else {
         GPX_TRY(gpx_potrf_block(h, diag, r.nb, r.wloc, dinvj, (int)r0));
