@@ -185,28 +185,35 @@ extern "C" int gpx_laplace_multi_step(gpx_handle h, const gpx_handle* lanes, int
     GPX_CUDA(cudaMemsetAsync(sd, 0, (size_t)C * np_ * sizeof(double), S));
     GPX_CUDA(cudaEventRecord(h->ev_a, S));
     // ---- per-class factorisations on the lanes (:88-101)
-    std::vector<int> used(nlanes, 0);
-    for (int i = 0; i < nloc; ++i) {
-        const int c = classes[i], k = i % nlanes;
-        gpx_ctx* e = lanes[k];
-        if (!used[k]) GPX_CUDA(cudaStreamWaitEvent(e->stream, h->ev_a, 0));
-        double* sdc = sd + (size_t)c * np_;
-        double* Lc = Linv_store + (size_t)i * sq;
-        GPX_TRY(gpx_vec_op(e, 10, n, 0.0, pi + (size_t)c * n, nullptr, nullptr, sdc));          // D_c^1/2
-        GPX_TRY(gpx_build_B(e, K, sdc, n, np_, ld, Lc));                                       // :92
-        double* dv = Ec[k];                                                                    // leaf inverses: head of Ec (overwritten by lauum later)
-        GPX_TRY(gpx_potrf_async(e, Lc, np_, np_, dv));                                         // :93  L_c
-        GPX_TRY(gpx_trtri(e, Lc, np_, np_, dv, Wk[k]));                                        // :94  L_c^-1
-        GPX_TRY(gpx_lauum(e, Lc, np_, np_, Ec[k], np_));                                       // B_c^-1 (lower tiles)
-        GPX_TRY(gpx_scale_sym_acc(e, Ec[k], sdc, n, np_, np_, used[k] ? 1 : 0, Es[k]));        // :95,:101
-        used[k] = 1;
-    }
+    std::vector<int> used(nlanes, 0), first_on_lane(nlanes, 1);
+    auto lanes_body = [&]() -> int {
+        for (int i = 0; i < nloc; ++i) {
+            const int c = classes[i], k = i % nlanes;
+            gpx_ctx* e = lanes[k];
+            if (!used[k]) GPX_CUDA(cudaStreamWaitEvent(e->stream, h->ev_a, 0));
+            used[k] = 1;                                                                           // from here on the lane must be joined
+            double* sdc = sd + (size_t)c * np_;
+            double* Lc = Linv_store + (size_t)i * sq;
+            GPX_TRY(gpx_vec_op(e, 10, n, 0.0, pi + (size_t)c * n, nullptr, nullptr, sdc));          // D_c^1/2
+            GPX_TRY(gpx_build_B(e, K, sdc, n, np_, ld, Lc));                                       // :92
+            double* dv = Ec[k];                                                                    // leaf inverses: head of Ec (overwritten by lauum later)
+            GPX_TRY(gpx_potrf_async(e, Lc, np_, np_, dv));                                         // :93  L_c
+            GPX_TRY(gpx_trtri(e, Lc, np_, np_, dv, Wk[k]));                                        // :94  L_c^-1
+            GPX_TRY(gpx_lauum(e, Lc, np_, np_, Ec[k], np_));                                       // B_c^-1 (lower tiles)
+            GPX_TRY(gpx_scale_sym_acc(e, Ec[k], sdc, n, np_, np_, first_on_lane[k] ? 0 : 1, Es[k])); // :95,:101
+            first_on_lane[k] = 0;
+        }
+        return 0;
+    };
+    const int lanes_rc = lanes_body();
+    // join every lane that was started back into S -- also on error, so that the caller never recycles the workspace while a
+    // lane is still writing it
     for (int k = 0; k < nlanes; ++k)
         if (used[k]) {
             gpx_ctx* e = lanes[k];
-            GPX_CUDA(cudaEventRecord(e->ev_b, e->stream));
-            GPX_CUDA(cudaStreamWaitEvent(S, e->ev_b, 0));
+            if (cudaEventRecord(e->ev_b, e->stream) == cudaSuccess) cudaStreamWaitEvent(S, e->ev_b, 0);
         }
+    GPX_TRY(lanes_rc);
     double* Esum = Es[0];
     if (!used[0]) GPX_CUDA(cudaMemsetAsync(Esum, 0, sq * sizeof(double), S));                  // this rank owns no class
     for (int k = 1; k < nlanes; ++k)
