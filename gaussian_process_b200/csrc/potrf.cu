@@ -4,6 +4,10 @@
 //            single-CTA shared-memory kernel that also emits the inverse of the leaf (used by every
 //            triangular solve as a GEMM operand); everything else is the DMMA GEMM of gemm.cu
 //            (TRSM against the leaf inverses, SYRK/GEMM trailing updates with k = half the block).
+//            Between 1024 and 16384 a three-stream look-ahead variant takes over (potrf_la_grouped): the panel chain
+//            factors leaves WITHOUT their inverses and solves by warp-per-row substitution (trsm_sub_kernel), the
+//            bulk of the trailing matrix is updated once per group of panels with K = G*128, and all leaf inverses
+//            come from one batched launch at the end.
 //   trsm   : recursive, left side, lower, N or T.
 //   trtri  : recursive in-place inverse of L (two triangular GEMMs per level, batched over the
 //            independent sub-problems of that level).

@@ -89,7 +89,8 @@ int gpx_co2_term(gpx_handle h, int term, int64_t rows, int64_t cols, const doubl
 /* ---- A4: Cholesky (np.linalg.cholesky call sites) ------------------------
  * In-place lower Cholesky of the n x n (n % 128 == 0) matrix A; on return the lower triangle holds
  * L and the strict upper triangle is zero (NumPy convention).  Blocked recursive right-looking:
- * 128x128 leaf factor (warp-shuffle/shared-memory kernel) + FP64 DMMA (mma.sync m8n8k4) TRSM/SYRK.
+ * 128x128 leaf factor (warp-shuffle/shared-memory kernel) + FP64 DMMA (mma.sync m8n8k4) TRSM/SYRK; for
+ * 1024 <= n <= 16384 a three-stream look-ahead variant (substitution panel chain + grouped K = G*128 updates).
  * `dinv` (n/128 tiles of 128x128, device) receives the inverses of the diagonal blocks of L; they
  * are required by the solve / inverse routines below. */
 int gpx_potrf(gpx_handle h, double* A, int64_t n, int64_t lda, double* dinv);
