@@ -814,8 +814,9 @@ int potrf_la_grouped(gpx_ctx* h, double* A, int64_t n, int64_t lda, double* dinv
     return rc;
 }
 
+int g_la_group_forced = -1;
 int la_group(int64_t n) {   // panels per group of the grouped look-ahead factorisation (0 / 1: ungrouped potrf_la_split)
-    static int forced = -1;
+    int& forced = g_la_group_forced;
     if (forced < 0) {
         const char* e = getenv("GPX_POTRF_LA_GROUP");
         forced = e ? atoi(e) : 0;
@@ -852,6 +853,13 @@ int la_threshold() {   // largest n factored by the look-ahead algorithm (0 disa
     return v;
 }
 }  // namespace
+
+// panels per group of the look-ahead factorisation: 0 = by size (default), 1 = ungrouped, G > 1 forces K = G*128 bulk updates
+extern "C" int gpx_potrf_set_group(int panels_per_group) {
+    GPX_REQUIRE(panels_per_group >= 0 && panels_per_group <= 64, 1);
+    g_la_group_forced = panels_per_group;
+    return 0;
+}
 
 extern "C" int gpx_potrf_async(gpx_handle h, double* A, int64_t n, int64_t lda, double* dinv) {
     GPX_ENTER(h);

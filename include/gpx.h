@@ -99,6 +99,9 @@ int gpx_potrf(gpx_handle h, double* A, int64_t n, int64_t lda, double* dinv);
  * (streams) factor independent matrices concurrently, e.g. the per-class B_c of GP_multi_classification.py:93. */
 int gpx_potrf_async(gpx_handle h, double* A, int64_t n, int64_t lda, double* dinv);
 int gpx_potrf_info(gpx_handle h, int* info_out);
+/* Tuning / test hook: panels per group of the look-ahead factorisation used for 1024 <= n <= 16384 (0 = chosen by size, the
+ * default; 1 = ungrouped; G > 1 = bulk trailing updates with K = G*128).  Process-wide. */
+int gpx_potrf_set_group(int panels_per_group);
 
 /* ---- A5: triangular solves (np.linalg.solve(L,.) / inv(L) call sites, row A5) -------------- */
 /* x <- L^-1 x (trans=0) or L^-T x (trans=1), one right-hand side, HBM-bound blocked TRSV. */

@@ -54,6 +54,42 @@ def test_potrf_matches_numpy(eng, n):
         assert rel(D[b] @ blk, np.eye(128)) < 1e-11
 
 
+@pytest.mark.parametrize("n,group", [(2432, 0), (4224, 0), (5248, 0), (2048, 4), (3200, 3)])
+def test_potrf_lookahead_groups_match_numpy(eng, n, group):
+    """The three-stream look-ahead factorisation (substitution chain, grouped K = G*128 bulk updates): panel counts that
+    leave a short last group (19, 33, 41 panels) with the default group sizes, and forced group sizes that do not divide
+    the panel count.  Factor, strict-upper zeros and the batched leaf inverses against NumPy."""
+    A = spd(n, seed=n)
+    Ad = eng.to_device(A)
+    assert eng.lib.gpx_potrf_set_group(group) == 0
+    try:
+        dinv = eng.potrf(Ad)
+    finally:
+        eng.lib.gpx_potrf_set_group(0)
+    L = np.linalg.cholesky(A)
+    Lg = eng.to_host(Ad)
+    assert np.all(np.triu(Lg, 1) == 0.0)
+    assert rel(Lg, L) < 1e-12
+    D = eng.to_host(dinv)
+    for b in (0, 1, n // 256, n // 128 - 1):
+        blk = L[b * 128:(b + 1) * 128, b * 128:(b + 1) * 128]
+        assert rel(D[b] @ blk, np.eye(128)) < 1e-11
+
+
+@pytest.mark.parametrize("n,bad", [(2048, 1500), (4224, 4200), (1152, 5)])
+def test_potrf_lookahead_not_positive_definite_reports_the_pivot(eng, n, bad):
+    """A failing pivot inside the look-ahead range (factor-only leaves on the chain stream): LinAlgError, as
+    np.linalg.cholesky raises, and the handle stays usable afterwards."""
+    A = spd(n, seed=7)
+    A[bad, bad] = -5.0
+    with pytest.raises(np.linalg.LinAlgError):
+        eng.potrf(eng.to_device(A))
+    B = spd(256, seed=8)
+    Bd = eng.to_device(B)
+    eng.potrf(Bd)
+    assert rel(eng.to_host(Bd), np.linalg.cholesky(B)) < 1e-12
+
+
 def test_potrf_not_positive_definite_raises(eng):
     A = spd(256, seed=3)
     A[200, 200] = -5.0
